@@ -1,0 +1,257 @@
+"""ctypes binding of libdvo.so (include/dvo.h).
+
+The shared library is the product: hand-written sm_100a CUDA behind a C ABI.  This module only moves pointers --
+PyTorch supplies device buffers and streams -- and it fails loudly when the library is missing or no CUDA device is
+usable.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdvo.so")
+
+DVO_MATCH_CROSSCHECK = 0
+DVO_MATCH_KNN_RATIO = 1
+PAIR_OK, PAIR_TOO_FEW_MATCHES, PAIR_NO_MODEL = 0, 1, 2
+
+
+class DvoError(RuntimeError):
+    pass
+
+
+class dvo_config(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int),
+                ("fast_threshold", ctypes.c_int), ("max_frames", ctypes.c_int), ("matcher", ctypes.c_int),
+                ("ransac_max_iters", ctypes.c_int), ("ransac_prob", ctypes.c_double), ("ransac_threshold", ctypes.c_double),
+                ("distance_thresh", ctypes.c_double), ("ratio", ctypes.c_float), ("use_tma", ctypes.c_int)]
+
+
+class dvo_features(ctypes.Structure):
+    _fields_ = [("d_pt", ctypes.c_void_p), ("d_size", ctypes.c_void_p), ("d_angle", ctypes.c_void_p),
+                ("d_response", ctypes.c_void_p), ("d_octave", ctypes.c_void_p), ("d_desc", ctypes.c_void_p),
+                ("d_count", ctypes.c_void_p), ("capacity", ctypes.c_int32)]
+
+
+class dvo_pair_arrays(ctypes.Structure):
+    _fields_ = [("d_matches", ctypes.c_void_p), ("d_pts_prev", ctypes.c_void_p), ("d_pts_cur", ctypes.c_void_p),
+                ("d_ransac_mask", ctypes.c_void_p), ("d_pose_mask", ctypes.c_void_p), ("capacity", ctypes.c_int32)]
+
+
+POSE_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("E", "<f8", (9,)), ("status", "<i4"), ("n_matches", "<i4"),
+                       ("n_inliers", "<i4"), ("n_good", "<i4"), ("ransac_iters", "<i4"), ("best_iter", "<i4"),
+                       ("candidate", "<i4"), ("n_prev", "<i4"), ("n_cur", "<i4"), ("reserved", "<i4")])
+assert POSE_DTYPE.itemsize == 208
+
+_lib = None
+
+
+def load_library():
+    """Load libdvo.so; raise if it was not built (``python -c 'import __graft_entry__ as g; g.build()'`` or ./build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise DvoError("libdvo.so not found at %s -- build it with ./build.sh (nvcc, sm_100a); there is no CPU fallback" % _LIB_PATH)
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.dvo_default_config.argtypes = [ctypes.POINTER(dvo_config)]
+    lib.dvo_default_config.restype = None
+    lib.dvo_create.argtypes = [ctypes.POINTER(dvo_config), ci, ctypes.POINTER(vp)]
+    lib.dvo_destroy.argtypes = [vp]
+    lib.dvo_destroy.restype = None
+    lib.dvo_last_error.argtypes = [vp]
+    lib.dvo_last_error.restype = ctypes.c_char_p
+    lib.dvo_version.restype = ctypes.c_char_p
+    lib.dvo_max_keypoints.argtypes = [vp]
+    lib.dvo_max_frames.argtypes = [vp]
+    lib.dvo_kernel_launches.argtypes = [vp]
+    lib.dvo_kernel_launches.restype = ctypes.c_longlong
+    lib.dvo_load_frames.argtypes = [vp, vp, ci, cs, cs, ci, ci, vp]
+    lib.dvo_orb.argtypes = [vp, ci, ci, vp]
+    lib.dvo_get_features.argtypes = [vp, ci, ctypes.POINTER(dvo_features), vp]
+    lib.dvo_pairs.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_get_poses.argtypes = [vp, ci, ci, vp, ci, vp]
+    lib.dvo_get_pair_arrays.argtypes = [vp, ci, ctypes.POINTER(dvo_pair_arrays), vp]
+    lib.dvo_sequence.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, vp]
+    lib.dvo_level_size.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.dvo_tap_image.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_tap_candidates.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci), vp]
+    lib.dvo_tap_ransac.argtypes = [vp, ci, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise DvoError("no CUDA device visible: the visual-odometry hot path runs only on the GPU (no CPU fallback)")
+    return torch
+
+
+class Context:
+    """One libdvo context bound to one GPU.  All methods enqueue on torch's current stream for that device."""
+
+    def __init__(self, width, height, nfeatures=500, nlevels=8, max_frames=2, matcher=DVO_MATCH_CROSSCHECK,
+                 ransac_max_iters=1000, ransac_prob=0.999, ransac_threshold=1.0, distance_thresh=50.0, ratio=0.75,
+                 fast_threshold=20, device=0, use_tma=True):
+        self.lib = load_library()
+        self.torch = _torch()
+        cfg = dvo_config()
+        self.lib.dvo_default_config(ctypes.byref(cfg))
+        cfg.width, cfg.height, cfg.nfeatures, cfg.nlevels = int(width), int(height), int(nfeatures), int(nlevels)
+        cfg.max_frames, cfg.matcher, cfg.ransac_max_iters = int(max_frames), int(matcher), int(ransac_max_iters)
+        cfg.ransac_prob, cfg.ransac_threshold, cfg.distance_thresh = float(ransac_prob), float(ransac_threshold), float(distance_thresh)
+        cfg.ratio, cfg.fast_threshold, cfg.use_tma = float(ratio), int(fast_threshold), int(bool(use_tma))
+        self.cfg = cfg
+        self.device = int(device)
+        self.width, self.height, self.nlevels = int(width), int(height), int(nlevels)
+        h = ctypes.c_void_p()
+        rc = self.lib.dvo_create(ctypes.byref(cfg), self.device, ctypes.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self.lib.dvo_last_error(h).decode() if h else "invalid configuration or no device"
+            if h:
+                self.lib.dvo_destroy(h)
+            self._h = None
+            raise DvoError("dvo_create failed (%d): %s" % (rc, msg))
+        self.max_keypoints = self.lib.dvo_max_keypoints(h)
+        self.max_frames = self.lib.dvo_max_frames(h)
+        self.tdev = self.torch.device("cuda", self.device)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dvo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DvoError("%s failed (%d): %s" % (what, rc, self.lib.dvo_last_error(self._h).decode()))
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.tdev).synchronize()
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.dvo_kernel_launches(self._h))
+
+    def level_size(self, level):
+        w, h, q = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.dvo_level_size(self._h, level, ctypes.byref(w), ctypes.byref(h), ctypes.byref(q)), "dvo_level_size")
+        return w.value, h.value, q.value
+
+    # ------------------------------------------------------------------ stages
+    def load_frames(self, frames, slot0=0):
+        """frames: (n, H, W) uint8 torch tensor (cuda or cpu) or numpy array (host)."""
+        t = self.torch
+        if isinstance(frames, np.ndarray):
+            frames = t.from_numpy(np.ascontiguousarray(frames))
+        if frames.dim() == 2:
+            frames = frames[None]
+        assert frames.dtype == t.uint8 and frames.shape[1] == self.height and frames.shape[2] == self.width
+        frames = frames.contiguous()
+        kind = 0 if frames.is_cuda else 1
+        self._check(self.lib.dvo_load_frames(self._h, frames.data_ptr(), frames.shape[0], self.width, self.width * self.height,
+                                             slot0, kind, self._stream()), "dvo_load_frames")
+        if kind == 1:
+            self.sync()   # host source must outlive the copy
+        return frames.shape[0]
+
+    def orb(self, slot0, n):
+        self._check(self.lib.dvo_orb(self._h, slot0, n, self._stream()), "dvo_orb")
+
+    def features(self, slot):
+        """Host copies of one slot's detectAndCompute output (synchronises)."""
+        t, M = self.torch, self.max_keypoints
+        pt = t.empty((M, 2), dtype=t.float32, device=self.tdev)
+        size = t.empty(M, dtype=t.float32, device=self.tdev)
+        angle = t.empty(M, dtype=t.float32, device=self.tdev)
+        resp = t.empty(M, dtype=t.float32, device=self.tdev)
+        octave = t.empty(M, dtype=t.int32, device=self.tdev)
+        desc = t.empty((M, 32), dtype=t.uint8, device=self.tdev)
+        count = t.zeros(1, dtype=t.int32, device=self.tdev)
+        f = dvo_features(pt.data_ptr(), size.data_ptr(), angle.data_ptr(), resp.data_ptr(), octave.data_ptr(), desc.data_ptr(),
+                         count.data_ptr(), M)
+        self._check(self.lib.dvo_get_features(self._h, slot, ctypes.byref(f), self._stream()), "dvo_get_features")
+        n = int(count.item())
+        return {"pt": pt[:n].cpu().numpy(), "size": size[:n].cpu().numpy(), "angle": angle[:n].cpu().numpy(),
+                "response": resp[:n].cpu().numpy(), "octave": octave[:n].cpu().numpy(), "desc": desc[:n].cpu().numpy()}
+
+    def pairs(self, slot0, pair0, n, K):
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        self._check(self.lib.dvo_pairs(self._h, slot0, pair0, n, Kc.ctypes.data, self._stream()), "dvo_pairs")
+
+    def poses(self, pair0, n):
+        out = np.zeros(n, dtype=POSE_DTYPE)
+        self._check(self.lib.dvo_get_poses(self._h, pair0, n, out.ctypes.data, 1, self._stream()), "dvo_get_poses")
+        self.sync()
+        return out
+
+    def pair_arrays(self, pair, n_matches):
+        t, M = self.torch, self.max_keypoints
+        matches = t.empty((M, 3), dtype=t.int32, device=self.tdev)
+        p1 = t.empty((M, 2), dtype=t.float32, device=self.tdev)
+        p2 = t.empty((M, 2), dtype=t.float32, device=self.tdev)
+        rm = t.empty(M, dtype=t.uint8, device=self.tdev)
+        pm = t.empty(M, dtype=t.uint8, device=self.tdev)
+        a = dvo_pair_arrays(matches.data_ptr(), p1.data_ptr(), p2.data_ptr(), rm.data_ptr(), pm.data_ptr(), M)
+        self._check(self.lib.dvo_get_pair_arrays(self._h, pair, ctypes.byref(a), self._stream()), "dvo_get_pair_arrays")
+        n = int(n_matches)
+        return {"matches": matches[:n].cpu().numpy(), "p_prev": p1[:n].cpu().numpy(), "p_cur": p2[:n].cpu().numpy(),
+                "ransac_mask": rm[:n].cpu().numpy(), "pose_mask": pm[:n].cpu().numpy()}
+
+    def sequence(self, frames, K, out=None):
+        """Consecutive-pair VO over all frames.  frames: (n, H, W) uint8, cuda tensor (poses come back through a device
+        buffer, one D2H at the end) or host tensor/ndarray (copies inside the call).  Returns POSE_DTYPE array (n-1,)."""
+        t = self.torch
+        if isinstance(frames, np.ndarray):
+            frames = t.from_numpy(np.ascontiguousarray(frames))
+        frames = frames.contiguous()
+        n = frames.shape[0]
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        if frames.is_cuda:
+            dposes = t.empty((n - 1) * POSE_DTYPE.itemsize, dtype=t.uint8, device=self.tdev) if out is None else out
+            self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+                                              dposes.data_ptr(), 0, self._stream()), "dvo_sequence")
+            if out is not None:
+                return out
+            return dposes.cpu().numpy().view(POSE_DTYPE)
+        poses = np.zeros(n - 1, dtype=POSE_DTYPE)
+        self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+                                          poses.ctypes.data, 1, self._stream()), "dvo_sequence")
+        return poses
+
+    # ------------------------------------------------------------------ taps
+    def tap_image(self, slot, level, which=0):
+        w, h, _ = self.level_size(level)
+        dst = self.torch.empty((h, w), dtype=self.torch.uint8, device=self.tdev)
+        self._check(self.lib.dvo_tap_image(self._h, slot, level, which, dst.data_ptr(), self._stream()), "dvo_tap_image")
+        return dst.cpu().numpy()
+
+    def tap_candidates(self, slot, level):
+        w, h, _ = self.level_size(level)
+        cap = ((w + 1) // 2) * ((h + 1) // 2)
+        dst = self.torch.empty(cap, dtype=self.torch.int32, device=self.tdev)
+        cnt = ctypes.c_int()
+        self._check(self.lib.dvo_tap_candidates(self._h, slot, level, dst.data_ptr(), cap, ctypes.byref(cnt), self._stream()),
+                    "dvo_tap_candidates")
+        v = dst[:cnt.value].cpu().numpy().view(np.uint32)
+        return np.stack([v & 0xFFF, (v >> 12) & 0xFFF, v >> 24], axis=1).astype(np.int32)
+
+    def tap_ransac(self, pair):
+        st = np.zeros(8, dtype=np.int32)
+        self._check(self.lib.dvo_tap_ransac(self._h, pair, st.ctypes.data, self._stream()), "dvo_tap_ransac")
+        return st

@@ -1,0 +1,483 @@
+// libdvo C ABI (include/dvo.h): context, HBM buffers, TMA tensor maps, stage taps, sequence runner.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include "dvo_internal.cuh"
+
+namespace dvo {
+long long orb_launch_count();
+long long pair_launch_count();
+void orb_kernels_init();
+void pair_kernels_init(int sortBytes);
+}  // namespace dvo
+
+using namespace dvo;
+
+struct dvo_ctx {
+    dvo_config cfg;
+    int device = 0;
+    std::string err;
+    OrbGeom og{};
+    OrbBuffers ob{};
+    PairGeom pg{};
+    PairBuffers pb{};
+    TensorMaps tmaps{};
+    bool useTma = false;
+    int nSlots = 0, nPairs = 0;
+    std::vector<void*> allocs;
+    uint32_t* d_resizeTab = nullptr;
+    double* d_K = nullptr;
+    dvo_pose* h_poseStage = nullptr;   // pinned staging for the host sequence runner
+    uint8_t* h_frameStage = nullptr;
+    long long launchBase = 0;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return DVO_E_CUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class T>
+static int dalloc(dvo_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return DVO_E_CUDA;
+    }
+    cudaMemset(q, 0, bytes);
+    ctx->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+// A.0 / A.4 geometry, in the float32 arithmetic cv2 uses
+static void build_geometry(dvo_ctx* ctx) {
+    const dvo_config& c = ctx->cfg;
+    OrbGeom& g = ctx->og;
+    g.nlevels = c.nlevels;
+    g.fastThreshold = c.fast_threshold;
+    const double sf = (double)1.2f;
+    // nfeaturesPerLevel
+    float factor = (float)(1.0 / sf);
+    float nd = (float)c.nfeatures * (1.0f - factor) / (1.0f - (float)std::pow((double)factor, (double)c.nlevels));
+    int quota[kMaxLevels], sum = 0;
+    for (int L = 0; L < c.nlevels - 1; ++L) {
+        quota[L] = (int)std::nearbyint(nd);
+        sum += quota[L];
+        nd = nd * factor;
+    }
+    quota[c.nlevels - 1] = std::max(c.nfeatures - sum, 0);
+    size_t off = 0;
+    int rowBase = 0, candBase = 0, finBase = 0, tileBase = 0, rbBase = 0;
+    for (int L = 0; L < c.nlevels; ++L) {
+        LevelGeom& lv = g.lv[L];
+        float scale = (float)std::pow(sf, (double)L);
+        lv.scale = scale;
+        lv.invScale = 1.0f / scale;
+        lv.w = (int)std::nearbyint(c.width * lv.invScale);
+        lv.h = (int)std::nearbyint(c.height * lv.invScale);
+        if (L == 0) { lv.w = c.width; lv.h = c.height; }
+        lv.pitch = (int)round_up(lv.w, 128);
+        lv.off = off;
+        off += round_up((size_t)lv.pitch * (lv.h + 1), 256);
+        lv.rowBase = rowBase;
+        rowBase += lv.h;
+        lv.quota = quota[L];
+        lv.candCap = ((lv.w + 1) / 2) * ((lv.h + 1) / 2);
+        lv.candBase = candBase;
+        candBase += (int)round_up(lv.candCap, 4);
+        lv.finCap = lv.quota + kFinSlack;
+        lv.finBase = finBase;
+        finBase += lv.finCap;
+        lv.tilesX = (lv.w + kTileW - 1) / kTileW;
+        lv.tilesY = (lv.h + kTileH - 1) / kTileH;
+        lv.tileBase = tileBase;
+        tileBase += lv.tilesX * lv.tilesY;
+        lv.rbBase = rbBase;
+        rbBase += (lv.h + 31) / 32;
+    }
+    g.slotStride = round_up(off, 1024);
+    g.rowsPerSlot = rowBase;
+    g.candPerSlot = candBase;
+    g.finPerSlot = finBase;
+    g.maxkp = finBase;
+    g.tilesPerFrame = tileBase;
+    g.rowBlocksPerFrame = rbBase;
+}
+
+// A.1 coefficient tables: per destination index, source offset and 8-bit weight of the right/lower neighbour
+static void resize_axis_table(int dst, int src, std::vector<uint32_t>& out) {
+    volatile double inv_scale = (double)dst / (double)src;
+    volatile double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        volatile double a = scale * (d + 0.5);
+        volatile double f = a - 0.5;
+        int i = (int)std::floor(f);
+        uint32_t ofs, c1;
+        if (i < 0) { ofs = 0; c1 = 0; }
+        else if (i >= src - 1) { ofs = (uint32_t)(src - 1); c1 = 0; }
+        else {
+            volatile double fr = (f - i) * 256.0;
+            ofs = (uint32_t)i;
+            c1 = (uint32_t)std::nearbyint(fr);
+        }
+        out.push_back((ofs << 16) | c1);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int build_tensor_maps(dvo_ctx* ctx) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        ctx->err = "cuTensorMapEncodeTiled not available from the driver";
+        return DVO_E_CUDA;
+    }
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+    for (int L = 0; L < ctx->og.nlevels; ++L) {
+        const LevelGeom& lv = ctx->og.lv[L];
+        cuuint64_t dims[3] = {(cuuint64_t)lv.w, (cuuint64_t)lv.h, (cuuint64_t)ctx->nSlots};
+        cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)ctx->og.slotStride};
+        cuuint32_t box[3] = {(cuuint32_t)kFastBoxW, (cuuint32_t)kFastBoxH, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&ctx->tmaps.pyr[L], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->ob.pyr + lv.off, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed for level %d: CUresult %d", L, (int)r);
+            ctx->err = buf;
+            return DVO_E_CUDA;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* dvo_version(void) { return "libdvo 0.1 (sm_100a)"; }
+
+void dvo_default_config(dvo_config* c) {
+    memset(c, 0, sizeof *c);
+    c->width = 1280; c->height = 1024;
+    c->nfeatures = 500; c->nlevels = 8; c->fast_threshold = 20;
+    c->max_frames = 2;
+    c->matcher = DVO_MATCH_CROSSCHECK;
+    c->ransac_max_iters = 1000; c->ransac_prob = 0.999; c->ransac_threshold = 1.0;
+    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1;
+}
+
+int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
+    if (!cfg || !out) return DVO_E_INVALID;
+    *out = nullptr;
+    if (cfg->width < 64 || cfg->height < 64 || cfg->width > kMaxImageDim || cfg->height > kMaxImageDim ||
+        cfg->nlevels < 1 || cfg->nlevels > kMaxLevels || cfg->nfeatures < 1 || cfg->nfeatures > 30000 || cfg->max_frames < 2 ||
+        cfg->ransac_max_iters < 1)
+        return DVO_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DVO_E_NODEVICE;
+    dvo_ctx* ctx = new dvo_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    *out = ctx;   // returned even on failure so the caller can read dvo_last_error, then dvo_destroy
+    CK(cudaSetDevice(device));
+    ctx->nSlots = cfg->max_frames;
+    ctx->nPairs = cfg->max_frames - 1;
+    build_geometry(ctx);
+    OrbGeom& g = ctx->og;
+    OrbBuffers& b = ctx->ob;
+    const size_t S = ctx->nSlots;
+    int rc;
+#define DA(p, n) if ((rc = dalloc(ctx, &(p), (n))) != 0) return rc
+    DA(b.pyr, S * g.slotStride + 4096);
+    DA(b.blur, S * g.slotStride + 4096);
+    DA(b.map, S * g.slotStride + 4096);
+    DA(b.rowCount, S * g.rowsPerSlot);
+    DA(b.cand, S * g.candPerSlot);
+    DA(b.candCount, S * kMaxLevels);
+    DA(b.pairs, S * g.candPerSlot);
+    DA(b.finXY, S * g.finPerSlot);
+    DA(b.finResp, S * g.finPerSlot);
+    DA(b.finCount, S * kMaxLevels);
+    DA(b.selDbg, S * kMaxLevels * 4);
+    DA(b.featPt, S * g.maxkp * 2);
+    DA(b.featResp, S * g.maxkp);
+    DA(b.featAngle, S * g.maxkp);
+    DA(b.featOctave, S * g.maxkp);
+    DA(b.featXY, S * g.maxkp);
+    DA(b.featDesc, S * g.maxkp * 32);
+    DA(b.featCount, S);
+    // resize tables
+    {
+        std::vector<uint32_t> tab;
+        for (int L = 0; L < g.nlevels; ++L) {
+            if (L == 0) { b.resizeTabOff[0][0] = b.resizeTabOff[0][1] = 0; continue; }
+            b.resizeTabOff[L][0] = (int)tab.size();
+            resize_axis_table(g.lv[L].w, g.lv[L - 1].w, tab);
+            b.resizeTabOff[L][1] = (int)tab.size();
+            resize_axis_table(g.lv[L].h, g.lv[L - 1].h, tab);
+        }
+        tab.push_back(0);
+        DA(ctx->d_resizeTab, tab.size());
+        CK(cudaMemcpy(ctx->d_resizeTab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        b.resizeTab = ctx->d_resizeTab;
+    }
+    // pair buffers
+    PairGeom& pg = ctx->pg;
+    PairBuffers& pb = ctx->pb;
+    pg.maxkp = g.maxkp;
+    pg.maxMatches = g.maxkp;
+    pg.sortCap = 1;
+    while (pg.sortCap < g.maxkp) pg.sortCap <<= 1;
+    pg.matcher = cfg->matcher;
+    pg.maxIters = cfg->ransac_max_iters;
+    pg.nChunks = (pg.maxIters + kRansacChunk - 1) / kRansacChunk;
+    pg.prob = cfg->ransac_prob;
+    pg.threshold = cfg->ransac_threshold;
+    pg.distThresh = cfg->distance_thresh;
+    pg.ratio = cfg->ratio;
+    const size_t P = ctx->nPairs, M = g.maxkp;
+    DA(pb.nnIdx, P * 2 * M);
+    DA(pb.nnDist, P * 2 * M);
+    DA(pb.nn2Dist, P * M);
+    DA(pb.matches, P * M * 3);
+    DA(pb.matchCount, P);
+    DA(pb.ptsPrev, P * M * 2);
+    DA(pb.ptsCur, P * M * 2);
+    DA(pb.normPts, P * M * 4);
+    DA(pb.samples, P * (size_t)pg.maxIters * 5);
+    DA(pb.models, P * (size_t)kRansacChunk * kMaxModels * 9);
+    DA(pb.modelCount, P * (size_t)kRansacChunk);
+    DA(pb.modelGood, P * (size_t)kRansacChunk * kMaxModels);
+    DA(pb.ransacState, P * 8);
+    DA(pb.bestE, P * 9);
+    DA(pb.ransacMask, P * M);
+    DA(pb.poseMask, P * M);
+    DA(pb.poses, P);
+    DA(pb.poseScratch, P);
+    DA(ctx->d_K, 16);
+#undef DA
+    ctx->useTma = cfg->use_tma != 0 && getenv("DVO_NO_TMA") == nullptr;
+    if (ctx->useTma) {
+        rc = build_tensor_maps(ctx);
+        if (rc != 0) return rc;
+    }
+    orb_kernels_init();
+    pair_kernels_init((int)(pg.sortCap * sizeof(uint32_t)));
+    CK(cudaDeviceSynchronize());
+    ctx->launchBase = orb_launch_count() + pair_launch_count();
+    return DVO_OK;
+}
+
+void dvo_destroy(dvo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->h_poseStage) cudaFreeHost(ctx->h_poseStage);
+    if (ctx->h_frameStage) cudaFreeHost(ctx->h_frameStage);
+    delete ctx;
+}
+
+const char* dvo_last_error(const dvo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int dvo_max_keypoints(const dvo_ctx* ctx) { return ctx ? ctx->og.maxkp : DVO_E_INVALID; }
+int dvo_max_frames(const dvo_ctx* ctx) { return ctx ? ctx->nSlots : DVO_E_INVALID; }
+long long dvo_kernel_launches(const dvo_ctx* ctx) {
+    return ctx ? orb_launch_count() + pair_launch_count() - ctx->launchBase : 0;
+}
+
+int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota) {
+    if (!ctx || level < 0 || level >= ctx->og.nlevels) return DVO_E_INVALID;
+    if (w) *w = ctx->og.lv[level].w;
+    if (h) *h = ctx->og.lv[level].h;
+    if (quota) *quota = ctx->og.lv[level].quota;
+    return DVO_OK;
+}
+
+int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, size_t frame_stride, int slot0, int kind,
+                    void* stream) {
+    if (!ctx || !frames || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots || pitch < (size_t)ctx->cfg.width) {
+        if (ctx) ctx->err = "dvo_load_frames: bad arguments";
+        return DVO_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const LevelGeom& l0 = ctx->og.lv[0];
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int i = 0; i < n; ++i) {
+        CK(cudaMemcpy2DAsync(ctx->ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
+                             frames + (size_t)i * frame_stride, pitch, l0.w, l0.h, k, st));
+    }
+    return DVO_OK;
+}
+
+int dvo_orb(dvo_ctx* ctx, int slot0, int n, void* stream) {
+    if (!ctx || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots) {
+        if (ctx) ctx->err = "dvo_orb: slot range out of bounds";
+        return DVO_E_INVALID;
+    }
+    launch_orb(ctx->og, ctx->ob, &ctx->tmaps, ctx->useTma, slot0, n, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+__global__ void k_fill_size(const int* octave, const int* count, float* size, int cap, float s0, float s1, float s2, float s3,
+                            float s4, float s5, float s6, float s7) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap || i >= *count) return;
+    const float sc[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+    size[i] = __fmul_rn(31.0f, sc[octave[i] & 7]);
+}
+
+int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stream) {
+    if (!ctx || !out || slot < 0 || slot >= ctx->nSlots) return DVO_E_INVALID;
+    if (out->capacity < ctx->og.maxkp) { ctx->err = "dvo_get_features: capacity < dvo_max_keypoints"; return DVO_E_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const OrbGeom& g = ctx->og;
+    const OrbBuffers& b = ctx->ob;
+    const size_t M = g.maxkp, o = (size_t)slot * M;
+    if (out->d_pt) CK(cudaMemcpyAsync(out->d_pt, b.featPt + o * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->d_angle) CK(cudaMemcpyAsync(out->d_angle, b.featAngle + o, M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->d_response) CK(cudaMemcpyAsync(out->d_response, b.featResp + o, M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->d_octave) CK(cudaMemcpyAsync(out->d_octave, b.featOctave + o, M * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (out->d_desc) CK(cudaMemcpyAsync(out->d_desc, b.featDesc + o * 32, M * 32, cudaMemcpyDeviceToDevice, st));
+    if (out->d_count) CK(cudaMemcpyAsync(out->d_count, b.featCount + slot, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (out->d_size) {
+        const LevelGeom* lv = g.lv;
+        k_fill_size<<<(int)((M + 255) / 256), 256, 0, st>>>(b.featOctave + o, b.featCount + slot, out->d_size, (int)M, lv[0].scale,
+                                                            lv[1].scale, lv[2].scale, lv[3].scale, lv[4].scale, lv[5].scale,
+                                                            lv[6].scale, lv[7].scale);
+        CK(cudaGetLastError());
+    }
+    return DVO_OK;
+}
+
+int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which, uint8_t* d_dst, void* stream) {
+    if (!ctx || !d_dst || slot < 0 || slot >= ctx->nSlots || level < 0 || level >= ctx->og.nlevels || which < 0 || which > 2)
+        return DVO_E_INVALID;
+    const LevelGeom& lv = ctx->og.lv[level];
+    const uint8_t* base = which == 0 ? ctx->ob.pyr : (which == 1 ? ctx->ob.blur : ctx->ob.map);
+    CK(cudaMemcpy2DAsync(d_dst, lv.w, base + (size_t)slot * ctx->og.slotStride + lv.off, lv.pitch, lv.w, lv.h,
+                         cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DVO_OK;
+}
+
+int dvo_tap_candidates(dvo_ctx* ctx, int slot, int level, uint32_t* d_dst, int capacity, int* h_count, void* stream) {
+    if (!ctx || slot < 0 || slot >= ctx->nSlots || level < 0 || level >= ctx->og.nlevels || !h_count) return DVO_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h_count, ctx->ob.candCount + slot * kMaxLevels + level, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*h_count > capacity) { ctx->err = "dvo_tap_candidates: capacity too small"; return DVO_E_CAPACITY; }
+    const LevelGeom& lv = ctx->og.lv[level];
+    if (d_dst && *h_count > 0)
+        CK(cudaMemcpyAsync(d_dst, ctx->ob.cand + (size_t)slot * ctx->og.candPerSlot + lv.candBase, sizeof(uint32_t) * (*h_count),
+                           cudaMemcpyDeviceToDevice, st));
+    return DVO_OK;
+}
+
+int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream) {
+    if (!ctx || !K || n < 0 || slot0 < 0 || slot0 + n + (n > 0 ? 1 : 0) > ctx->nSlots || pair0 < 0 || pair0 + n > ctx->nPairs) {
+        if (ctx) ctx->err = "dvo_pairs: slot/pair range out of bounds";
+        return DVO_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_pairs(ctx->og, ctx->ob, ctx->pg, ctx->pb, slot0, pair0, n, K, st);
+    CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+int dvo_get_poses(dvo_ctx* ctx, int pair0, int n, dvo_pose* dst, int kind, void* stream) {
+    if (!ctx || !dst || n < 0 || pair0 < 0 || pair0 + n > ctx->nPairs) return DVO_E_INVALID;
+    CK(cudaMemcpyAsync(dst, ctx->pb.poses + pair0, sizeof(dvo_pose) * n, kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    return DVO_OK;
+}
+
+int dvo_get_pair_arrays(dvo_ctx* ctx, int pair, const dvo_pair_arrays* out, void* stream) {
+    if (!ctx || !out || pair < 0 || pair >= ctx->nPairs) return DVO_E_INVALID;
+    if (out->capacity < ctx->og.maxkp) { ctx->err = "dvo_get_pair_arrays: capacity < dvo_max_keypoints"; return DVO_E_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t M = ctx->og.maxkp, o = (size_t)pair * M;
+    const PairBuffers& pb = ctx->pb;
+    if (out->d_matches) CK(cudaMemcpyAsync(out->d_matches, pb.matches + o * 3, M * 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (out->d_pts_prev) CK(cudaMemcpyAsync(out->d_pts_prev, pb.ptsPrev + o * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->d_pts_cur) CK(cudaMemcpyAsync(out->d_pts_cur, pb.ptsCur + o * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->d_ransac_mask) CK(cudaMemcpyAsync(out->d_ransac_mask, pb.ransacMask + o, M, cudaMemcpyDeviceToDevice, st));
+    if (out->d_pose_mask) CK(cudaMemcpyAsync(out->d_pose_mask, pb.poseMask + o, M, cudaMemcpyDeviceToDevice, st));
+    return DVO_OK;
+}
+
+int dvo_tap_ransac(dvo_ctx* ctx, int pair, int32_t* h_state8, void* stream) {
+    if (!ctx || !h_state8 || pair < 0 || pair >= ctx->nPairs) return DVO_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h_state8, ctx->pb.ransacState + pair * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DVO_OK;
+}
+
+__global__ void k_copy_features(OrbGeom g, OrbBuffers b, int src, int dst) {
+    // carry the last frame of a batch into slot 0 for the next batch
+    const int M = g.maxkp;
+    const size_t so = (size_t)src * M, d0 = (size_t)dst * M;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * 8; i += gridDim.x * blockDim.x) {
+        reinterpret_cast<uint32_t*>(b.featDesc + d0 * 32)[i] = reinterpret_cast<const uint32_t*>(b.featDesc + so * 32)[i];
+        if (i < M * 2) b.featPt[d0 * 2 + i] = b.featPt[so * 2 + i];
+        if (i < M) {
+            b.featResp[d0 + i] = b.featResp[so + i];
+            b.featAngle[d0 + i] = b.featAngle[so + i];
+            b.featOctave[d0 + i] = b.featOctave[so + i];
+            b.featXY[d0 + i] = b.featXY[so + i];
+        }
+        if (i == 0) b.featCount[dst] = b.featCount[src];
+    }
+}
+
+int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride, const double* K,
+                 dvo_pose* poses, int kind, void* stream) {
+    if (!ctx || !frames || !K || !poses || n_frames < 2) {
+        if (ctx) ctx->err = "dvo_sequence: bad arguments";
+        return DVO_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = ctx->nSlots - 1;   // new frames per batch after the first
+    int done = 0;                    // frames whose features exist
+    int rc;
+    // first batch: up to nSlots frames into slots 0..
+    int n0 = std::min(n_frames, ctx->nSlots);
+    if ((rc = dvo_load_frames(ctx, frames, n0, pitch, frame_stride, 0, kind, st)) != 0) return rc;
+    if ((rc = dvo_orb(ctx, 0, n0, st)) != 0) return rc;
+    if ((rc = dvo_pairs(ctx, 0, 0, n0 - 1, K, st)) != 0) return rc;
+    if ((rc = dvo_get_poses(ctx, 0, n0 - 1, poses, kind, st)) != 0) return rc;
+    done = n0;
+    int carry = n0 - 1;              // slot holding the last processed frame's features
+    while (done < n_frames) {
+        int nb = std::min(B, n_frames - done);
+        if (carry != 0) {
+            k_copy_features<<<32, 256, 0, st>>>(ctx->og, ctx->ob, carry, 0);
+            CK(cudaGetLastError());
+        }
+        if ((rc = dvo_load_frames(ctx, frames + (size_t)done * frame_stride, nb, pitch, frame_stride, 1, kind, st)) != 0) return rc;
+        if ((rc = dvo_orb(ctx, 1, nb, st)) != 0) return rc;
+        if ((rc = dvo_pairs(ctx, 0, 0, nb, K, st)) != 0) return rc;
+        if ((rc = dvo_get_poses(ctx, 0, nb, poses + (done - 1), kind, st)) != 0) return rc;
+        carry = nb;
+        done += nb;
+    }
+    if (kind == 1) CK(cudaStreamSynchronize(st));
+    return DVO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Internal layout of a dvo context: HBM buffers, per-level geometry, kernel launch entry points.
+//
+// HBM layout (DESIGN.md "Data layout"): everything is per frame SLOT (one slot per frame in flight).
+//   pyr / blur / map : u8 images, 8 levels each, row pitch = roundup(w, 128), levels 256-B aligned, slot stride fixed
+//   rowCount         : int32 per pyramid row (survivor count after NMS), zeroed per batch
+//   cand             : u32 per candidate, packed score<<24 | y<<12 | x, raster order per level
+//   pairs            : u64 per first-cut survivor, harris f32 bits <<32 | packed xy, cv2 order
+//   fin*             : final keypoints per level in cv2 order
+//   feat*            : per-frame compact feature arrays (what cv2 returns from detectAndCompute)
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/dvo.h"
+
+namespace dvo {
+
+constexpr int kMaxLevels = 8;
+constexpr int kTileW = 128;          // image-kernel tile (outputs)
+constexpr int kTileH = 32;
+constexpr int kFastHaloL = 16;       // TMA needs the inner start coordinate 16-byte aligned: left halo is 16 px (4 used)
+constexpr int kFastBoxW = 160;       // TMA box: 16 + tile + 16 (multiple of 16 bytes)
+constexpr int kFastBoxH = 40;
+constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
+constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
+constexpr int kSelectSmemBytes = 64 * 1024;
+constexpr int kRansacChunk = 128;    // RANSAC iterations solved+scored per launch group
+constexpr int kMaxModels = 10;
+
+struct LevelGeom {
+    int w, h, pitch;
+    int rowBase;         // first row in the per-slot row arrays
+    int quota;           // nfeaturesPerLevel
+    int candCap, candBase;
+    int finCap, finBase;
+    int tilesX, tilesY, tileBase;
+    int rbBase;          // first 32-row block in the per-slot row-block index space
+    float scale, invScale;
+    unsigned long long off;   // byte offset inside a slot's image buffer
+};
+
+struct OrbGeom {
+    int nlevels;
+    int rowsPerSlot, candPerSlot, finPerSlot, maxkp;
+    int tilesPerFrame, rowBlocksPerFrame;
+    int fastThreshold;
+    unsigned long long slotStride;   // bytes between slots in pyr/blur/map
+    LevelGeom lv[kMaxLevels];
+};
+
+struct OrbBuffers {
+    uint8_t* pyr;
+    uint8_t* blur;
+    uint8_t* map;
+    int* rowCount;           // [slots][rowsPerSlot]
+    uint32_t* cand;          // [slots][candPerSlot]
+    int* candCount;          // [slots][8]
+    unsigned long long* pairs;   // [slots][candPerSlot]
+    uint32_t* finXY;         // [slots][finPerSlot]
+    float* finResp;          // [slots][finPerSlot]
+    int* finCount;           // [slots][8]
+    int* selDbg;             // [slots][8][4]: n candidates, n after fast cut, n final, flags
+    // compact per-frame features
+    float* featPt;           // [slots][maxkp][2]
+    float* featResp;         // [slots][maxkp]
+    float* featAngle;        // [slots][maxkp]
+    int* featOctave;         // [slots][maxkp]
+    uint32_t* featXY;        // [slots][maxkp] packed level coords
+    uint8_t* featDesc;       // [slots][maxkp][32]
+    int* featCount;          // [slots]
+    const uint32_t* resizeTab;   // per level: x table then y table, packed ofs<<16 | c1
+    int resizeTabOff[kMaxLevels][2];
+};
+
+struct TensorMaps {
+    CUtensorMap pyr[kMaxLevels];
+};
+
+struct PairGeom {
+    int maxkp;            // descriptor capacity per slot
+    int maxMatches;       // == maxkp
+    int sortCap;          // power of two >= maxkp
+    int matcher;          // 0 crosscheck, 1 knn ratio + reverse check
+    int maxIters;
+    int nChunks;
+    double prob, threshold, distThresh;
+    float ratio;
+};
+
+// per-pair scratch carried between the three pose kernels
+struct PoseScratch { double R1[9], R2[9], t[3]; int good[4]; int nInl; int pad[3]; };
+
+struct PairBuffers {
+    // per pair slot
+    int* nnIdx;           // [pairs][2 dirs][maxkp]      best index
+    int* nnDist;          // [pairs][2][maxkp]
+    int* nn2Dist;         // [pairs][maxkp]              second-best distance (forward only, knn mode)
+    int* matches;         // [pairs][maxkp][3]           (queryIdx, trainIdx, distance) sorted by (distance, queryIdx)
+    int* matchCount;      // [pairs]
+    float* ptsPrev;       // [pairs][maxkp][2]
+    float* ptsCur;        // [pairs][maxkp][2]
+    double* normPts;      // [pairs][maxkp][4]           x1 y1 x2 y2 normalised
+    int* samples;         // [pairs][maxIters][5]
+    double* models;       // [pairs][chunk][10][9]
+    int* modelCount;      // [pairs][chunk]
+    int* modelGood;       // [pairs][chunk][10]
+    int* ransacState;     // [pairs][8]: maxGood, niters, done, bestIter, bestModel, itersRun, modelsScored, hasBest
+    double* bestE;        // [pairs][9]
+    uint8_t* ransacMask;  // [pairs][maxkp]
+    uint8_t* poseMask;    // [pairs][maxkp]
+    dvo_pose* poses;      // [pairs]
+    PoseScratch* poseScratch;   // [pairs]
+};
+
+// ---- launchers (orb_kernels.cu / pair_kernels.cu) ---------------------------------------------------------------
+void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
+                cudaStream_t st);
+void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
+                  int pair0, int nPairs, const double* K, cudaStream_t st);
+
+}  // namespace dvo

@@ -1,0 +1,623 @@
+// ORB detect + describe on sm_100a: the cv2 stages behind feature_detector.detectAndCompute
+// (/root/reference/scripts/visual_odometry_v3.py:373).  Bit-exact contract: SURVEY.md Appendix A.1-A.7.
+//
+// Kernels (one launch each per batch of frame slots; blockIdx.y / .z carries the slot):
+//   k_pyr_down      A.1  INTER_LINEAR_EXACT chained down-scale, one launch per level
+//   k_fast_nms      A.2  FAST-9/16 score + strict 3x3 NMS, tile staged by TMA (cp.async.bulk.tensor) into smem
+//   k_compact       A.2  raster-order compaction of NMS survivors (warp ballot-free prefix by shuffles)
+//   k_select        A.3/A.4  retainBest(2N) on FAST score, Harris, retainBest(N), order-exact (select.cuh)
+//   k_angle_pack    A.5  intensity-centroid angle + per-frame feature packing
+//   k_blur          A.6  7x7 sigma-2 separable Gaussian, float32 FMA order of cv2's filter engine
+//   k_brief         A.7  steered BRIEF-256
+#include "dvo_internal.cuh"
+#include "mathcore.cuh"
+#include "select.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+namespace dvo {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
+    int L = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < g.nlevels && tile >= g.lv[i].tileBase) L = i;
+    return L;
+}
+
+// =========================================================================================== A.1 pyramid
+__global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0) {
+    const LevelGeom& d = g.lv[L];
+    const LevelGeom& s = g.lv[L - 1];
+    const int slot = slot0 + blockIdx.z;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x4 >= d.w || y >= d.h) return;
+    const uint32_t* tx = b.resizeTab + b.resizeTabOff[L][0];
+    const uint32_t* ty = b.resizeTab + b.resizeTabOff[L][1];
+    const uint8_t* src = b.pyr + (size_t)slot * g.slotStride + s.off;
+    uint8_t* dst = b.pyr + (size_t)slot * g.slotStride + d.off;
+    const uint32_t ey = __ldg(ty + y);
+    const int oy = ey >> 16, cy1 = ey & 0xFFFF, cy0 = 256 - cy1;
+    const int oy1 = min(oy + 1, s.h - 1);
+    const uint8_t* r0 = src + (size_t)oy * s.pitch;
+    const uint8_t* r1 = src + (size_t)oy1 * s.pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int x = x4 + k;
+        if (x < d.w) {
+            const uint32_t ex = __ldg(tx + x);
+            const int ox = ex >> 16, cx1 = ex & 0xFFFF, cx0 = 256 - cx1;
+            const int ox1 = min(ox + 1, s.w - 1);
+            int h0 = cx0 * (int)__ldg(r0 + ox) + cx1 * (int)__ldg(r0 + ox1);
+            int h1 = cx0 * (int)__ldg(r1 + ox) + cx1 * (int)__ldg(r1 + ox1);
+            int v = (h0 * cy0 + h1 * cy1 + (1 << 15)) >> 16;
+            out |= (uint32_t)v << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x4) = out;
+}
+
+// =========================================================================================== A.2 FAST + NMS
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool kUseTma>
+__global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
+    __shared__ __align__(128) uint8_t raw[kFastBoxH * kFastBoxW];
+    __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
+    __shared__ __align__(8) unsigned long long bar;
+
+    const int tile = blockIdx.x;
+    const int L = find_level_by_tile(g, tile);
+    const LevelGeom lv = g.lv[L];
+    const int t = tile - lv.tileBase;
+    const int tx = t % lv.tilesX, ty = t / lv.tilesX;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int slot = slot0 + blockIdx.y;
+    const int tid = threadIdx.x;
+
+    if (kUseTma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
+                         "r"(kFastBoxH * kFastBoxW)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                    smem_u32(raw)),
+                "l"(reinterpret_cast<uint64_t>(&tm.pyr[L])), "r"(smem_u32(&bar)), "r"(x0 - kFastHaloL), "r"(y0 - 4), "r"(slot)
+                : "memory");
+        }
+        // all threads wait for the bytes to land (phase 0)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smem_u32(&bar)),
+            "r"(0)
+            : "memory");
+    } else {
+        const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
+        for (int i = tid; i < kFastBoxH * (kFastBoxW / 4); i += 256) {
+            int ry = i / (kFastBoxW / 4), rw = i % (kFastBoxW / 4);
+            int gy = y0 - 4 + ry, gx = x0 - kFastHaloL + rw * 4;
+            uint32_t v = 0;
+            if (gy >= 0 && gy < lv.h && gx >= 0 && gx < lv.pitch) {
+                v = *reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx);
+                // zero bytes at x >= w like TMA's out-of-bounds fill
+                if (gx + 3 >= lv.w) {
+                    uint32_t keep = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if (gx + k < lv.w) keep |= 0xFFu << (8 * k);
+                    v &= keep;
+                }
+            }
+            *reinterpret_cast<uint32_t*>(raw + ry * kFastBoxW + rw * 4) = v;
+        }
+        __syncthreads();
+    }
+
+    // scores on the (tile + 1) ring: 130 x 34 positions, sx = x0-1+cx, sy = y0-1+cy
+    const int dxs[16] = DVO_FAST_DX, dys[16] = DVO_FAST_DY;
+    for (int i = tid; i < (kTileH + 2) * (kTileW + 2); i += 256) {
+        int cy = i / (kTileW + 2), cx = i % (kTileW + 2);
+        int sx = x0 - 1 + cx, sy = y0 - 1 + cy;
+        int score = 0;
+        if (sx >= 3 && sx < lv.w - 3 && sy >= 3 && sy < lv.h - 3) {
+            const uint8_t* c = raw + (cy + 3) * kFastBoxW + (cx + kFastHaloL - 1);
+            int v = *c;
+            // cheap reject: a 9-arc always contains one of every opposite pair
+            int d0 = v - c[3 * kFastBoxW], d8 = v - c[-3 * kFastBoxW];
+            int th = g.fastThreshold;
+            if (abs(d0) > th || abs(d8) > th) {
+                int p[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) p[k] = c[dys[k] * kFastBoxW + dxs[k]];
+                score = fast_score16(v, p, th);
+#ifdef DVO_DBG_FAST
+                if (L == 0 && slot == 0 && sx == 155 && sy == 31) {
+                    printf("DBG v=%d th=%d score=%d cx=%d cy=%d x0=%d y0=%d p:", v, th, score, cx, cy, x0, y0);
+                    for (int k = 0; k < 16; ++k) printf(" %d", p[k]);
+                    printf("\n");
+                }
+#endif
+            }
+        }
+        sc[cy * 136 + cx] = (uint8_t)score;
+    }
+    __syncthreads();
+
+    // NMS + write map + per-row survivor counts
+    uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
+    int* rowCount = b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int border = 31;
+    for (int r = warp; r < kTileH; r += 8) {
+        int y = y0 + r;
+        if (y >= lv.h) break;
+        uint32_t word = 0;
+        int cnt = 0;
+        bool rowIn = (y >= border && y < lv.h - border);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cx = lane * 4 + k + 1, cy = r + 1;
+            int x = x0 + lane * 4 + k;
+            int s = sc[cy * 136 + cx];
+            bool keep = rowIn && s > 0 && x >= border && x < lv.w - border;
+            if (keep) {
+                const uint8_t* q = sc + cy * 136 + cx;
+                keep = s > q[-1] && s > q[1] && s > q[-136 - 1] && s > q[-136] && s > q[-136 + 1] && s > q[136 - 1] &&
+                       s > q[136] && s > q[136 + 1];
+            }
+            if (keep) {
+                word |= (uint32_t)s << (8 * k);
+                ++cnt;
+            }
+        }
+        int xw = x0 + lane * 4;
+        if (xw < lv.pitch) *reinterpret_cast<uint32_t*>(map + (size_t)y * lv.pitch + xw) = word;
+        int total = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && total > 0) atomicAdd(rowCount + y, total);
+    }
+}
+
+// =========================================================================================== compaction
+__global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int slot0) {
+    __shared__ int s_red[8];
+    __shared__ int s_rowOff[33];
+    const int rb = blockIdx.x;
+    int L = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < g.nlevels && rb >= g.lv[i].rbBase) L = i;
+    const LevelGeom lv = g.lv[L];
+    const int slot = slot0 + blockIdx.y;
+    const int row0 = (rb - lv.rbBase) * 32;
+    const int* rowCount = b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // base = sum of counts of rows [0, row0)
+    int acc = 0;
+    for (int r = tid; r < row0; r += 256) acc += rowCount[r];
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        int base = 0;
+        for (int i = 0; i < 8; ++i) base += s_red[i];
+        int r = row0 + lane;
+        int c = (r < lv.h) ? rowCount[r] : 0;
+        // exclusive scan over the 32 rows
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        s_rowOff[lane] = base + incl - c;
+        if (lane == 31) s_rowOff[32] = base + incl;
+    }
+    __syncthreads();
+    if (row0 + 32 >= lv.h && tid == 0) b.candCount[slot * kMaxLevels + L] = s_rowOff[32];
+
+    const uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
+    uint32_t* cand = b.cand + (size_t)slot * g.candPerSlot + lv.candBase;
+    for (int rr = warp; rr < 32; rr += 8) {
+        int y = row0 + rr;
+        if (y >= lv.h) break;
+        int n = s_rowOff[rr + 1] - s_rowOff[rr];
+        if (n == 0) continue;
+        int running = s_rowOff[rr];
+        for (int xc = 0; xc < lv.w; xc += 128) {
+            int x = xc + lane * 4;
+            uint32_t word = 0;
+            if (x < lv.pitch) word = *reinterpret_cast<const uint32_t*>(map + (size_t)y * lv.pitch + x);
+            int c = ((word & 0xFFu) != 0) + ((word & 0xFF00u) != 0) + ((word & 0xFF0000u) != 0) + ((word & 0xFF000000u) != 0);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int nn = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nn;
+            }
+            int pos = running + incl - c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t s = (word >> (8 * k)) & 0xFFu;
+                if (s) {
+                    if (pos < lv.candCap) cand[pos] = (s << 24) | ((uint32_t)y << 12) | (uint32_t)(x + k);
+                    ++pos;
+                }
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+// =========================================================================================== selection
+// Accessor used by select.cuh on the device: the whole warp executes the replay with identical scalar state; element
+// writes are done by lane 0, the two Hoare scan loops look at 32 elements per step.
+template <class T, class Key>
+struct WarpAcc {
+    typedef T Item;
+    T* d;
+    int n;   // array length: scans never read outside [0, n)
+    __device__ __forceinline__ T get(int i) const { return d[i]; }
+    __device__ __forceinline__ void set(int i, T v) {
+        if (lane_id() == 0) d[i] = v;
+        __syncwarp();
+    }
+    __device__ __forceinline__ static bool gt(T a, T b) { return Key::key(a) > Key::key(b); }
+    __device__ __forceinline__ int scan_up(int first, T pivot) const {
+        while (true) {
+            int i = first + lane_id();
+            bool stop = (i >= n) || !gt(d[i], pivot);
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return first + __ffs(m) - 1;
+            first += 32;
+        }
+    }
+    __device__ __forceinline__ int scan_down(int last, T pivot) const {
+        while (true) {
+            int i = last - lane_id();
+            bool stop = (i < 0) || !gt(pivot, d[i]);
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return last - (__ffs(m) - 1);
+            last -= 32;
+        }
+    }
+    __device__ __forceinline__ int scan_up_ge(int first, int last, T bnd) const {
+        while (true) {
+            int i = first + lane_id();
+            bool stop = (i >= last) || !(Key::key(d[i]) >= Key::key(bnd));
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return min(first + __ffs(m) - 1, last);
+            first += 32;
+        }
+    }
+    __device__ __forceinline__ int scan_down_lt(int first, int last, T bnd) const {
+        while (true) {
+            int i = last - lane_id();
+            bool stop = (i <= first) || (Key::key(d[i]) >= Key::key(bnd));
+            unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return max(last - (__ffs(m) - 1), first);
+            last -= 32;
+        }
+    }
+};
+
+struct KeyScore {   // packed candidate: FAST score in the top byte
+    __device__ __forceinline__ static int key(uint32_t v) { return (int)(v >> 24); }
+};
+struct KeyHarris {  // harris float bits in the high word
+    __device__ __forceinline__ static float key(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+};
+
+__device__ __forceinline__ int harris_sums_warp(const uint8_t* img, int pitch, int x, int y, int lane, int& b_out, int& c_out) {
+    // 7x7 block of Sobel-3 products: lanes 0..48 (two rounds) each take one block pixel
+    int a = 0, bb = 0, c = 0;
+    for (int i = lane; i < 49; i += 32) {
+        int dy = i / 7 - 3, dx = i % 7 - 3;
+        const uint8_t* p = img + (size_t)(y + dy) * pitch + (x + dx);
+        int p00 = p[-pitch - 1], p01 = p[-pitch], p02 = p[-pitch + 1];
+        int p10 = p[-1], p12 = p[1];
+        int p20 = p[pitch - 1], p21 = p[pitch], p22 = p[pitch + 1];
+        int ix = (p12 - p10) * 2 + (p02 - p00) + (p22 - p20);
+        int iy = (p21 - p01) * 2 + (p20 - p00) + (p22 - p02);
+        a += ix * ix;
+        bb += iy * iy;
+        c += ix * iy;
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    bb = __reduce_add_sync(0xffffffffu, bb);
+    c = __reduce_add_sync(0xffffffffu, c);
+    b_out = bb;
+    c_out = c;
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_select(OrbGeom g, OrbBuffers b, int slot0) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ int s_n1, s_n2;
+    const int L = blockIdx.x;
+    const int slot = slot0 + blockIdx.y;
+    const LevelGeom lv = g.lv[L];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t* cand = b.cand + (size_t)slot * g.candPerSlot + lv.candBase;
+    unsigned long long* pairs = b.pairs + (size_t)slot * g.candPerSlot + lv.candBase;
+    int n = min(b.candCount[slot * kMaxLevels + L], lv.candCap);
+
+    // ---- pass 1: retainBest(2 * quota) on the FAST score, order-exact
+    const bool inSmem1 = (size_t)n * sizeof(uint32_t) <= (size_t)kSelectSmemBytes;
+    uint32_t* work1 = inSmem1 ? reinterpret_cast<uint32_t*>(s_dyn) : cand;
+    if (inSmem1) {
+        for (int i = tid; i < n; i += 256) work1[i] = cand[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        WarpAcc<uint32_t, KeyScore> acc{work1, n};
+        int n1 = retain_best_replay(acc, n, 2 * lv.quota);
+        if (lane == 0) s_n1 = n1;
+    }
+    __syncthreads();
+    const int n1 = s_n1;
+
+    // ---- Harris response of the survivors (un-blurred level)
+    const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
+    for (int i = warp; i < n1; i += 8) {
+        uint32_t c = work1[i];
+        int x = c & 0xFFF, y = (c >> 12) & 0xFFF;
+        int sb, sc_;
+        int sa = harris_sums_warp(img, lv.pitch, x, y, lane, sb, sc_);
+        if (lane == 0) {
+            float r = harris_from_sums(sa, sb, sc_);
+            pairs[i] = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(c & 0xFFFFFFu);
+        }
+    }
+    __syncthreads();   // pairs[] written with plain stores by this block, read back below after the barrier
+
+    // ---- pass 2: retainBest(quota) on Harris, order-exact
+    const bool inSmem2 = (size_t)n1 * sizeof(unsigned long long) <= (size_t)kSelectSmemBytes;
+    unsigned long long* work2 = inSmem2 ? reinterpret_cast<unsigned long long*>(s_dyn) : pairs;
+    if (inSmem2) {
+        for (int i = tid; i < n1; i += 256) work2[i] = pairs[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        WarpAcc<unsigned long long, KeyHarris> acc{work2, n1};
+        int n2 = retain_best_replay(acc, n1, lv.quota);
+        if (lane == 0) s_n2 = n2;
+    }
+    __syncthreads();
+    int n2 = s_n2;
+    int flags = 0;
+    if (n2 > lv.finCap) { n2 = lv.finCap; flags |= 1; }
+    uint32_t* finXY = b.finXY + (size_t)slot * g.finPerSlot + lv.finBase;
+    float* finResp = b.finResp + (size_t)slot * g.finPerSlot + lv.finBase;
+    for (int i = tid; i < n2; i += 256) {
+        unsigned long long v = work2[i];
+        finXY[i] = (uint32_t)(v & 0xFFFFFFu);
+        finResp[i] = __uint_as_float((uint32_t)(v >> 32));
+    }
+    if (tid == 0) {
+        b.finCount[slot * kMaxLevels + L] = n2;
+        int* dbg = b.selDbg + (slot * kMaxLevels + L) * 4;
+        dbg[0] = n; dbg[1] = n1; dbg[2] = n2; dbg[3] = flags;
+    }
+}
+
+// =========================================================================================== A.5 angle + pack
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__global__ void __launch_bounds__(256) k_angle_pack(OrbGeom g, OrbBuffers b, int slot0) {
+    const int slot = slot0 + blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.x * 8 + warp;
+    int total = 0, L = -1, idx = 0;
+    const int* finCount = b.finCount + slot * kMaxLevels;
+    for (int i = 0; i < g.nlevels; ++i) {
+        int c = finCount[i];
+        if (L < 0 && gi < total + c) { L = i; idx = gi - total; }
+        total += c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.featCount[slot] = min(total, g.maxkp);
+    if (L < 0 || gi >= g.maxkp) return;
+    const LevelGeom lv = g.lv[L];
+    const uint32_t xy = b.finXY[(size_t)slot * g.finPerSlot + lv.finBase + idx];
+    const float resp = b.finResp[(size_t)slot * g.finPerSlot + lv.finBase + idx];
+    const int x = xy & 0xFFF, y = (xy >> 12) & 0xFFF;
+    const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
+    // lanes 0..30 own column u = lane - 15
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int au = abs(u);
+        const uint8_t* c = img + (size_t)y * lv.pitch + x + u;
+        m10 = u * (int)c[0];
+        for (int v = 1; v <= 15; ++v) {
+            if (au <= c_umax[v]) {
+                int vp = c[v * lv.pitch], vm = c[-v * lv.pitch];
+                m10 += u * (vp + vm);
+                m01 += v * (vp - vm);
+            }
+        }
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    if (lane == 0) {
+        float ang = fast_atan2_deg((float)m01, (float)m10);
+        size_t o = (size_t)slot * g.maxkp + gi;
+        b.featPt[o * 2 + 0] = fmul((float)x, lv.scale);
+        b.featPt[o * 2 + 1] = fmul((float)y, lv.scale);
+        b.featResp[o] = resp;
+        b.featAngle[o] = ang;
+        b.featOctave[o] = L;
+        b.featXY[o] = xy;
+    }
+}
+
+// =========================================================================================== A.6 blur
+__global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0) {
+    __shared__ uint8_t raw[(kTileH + 6) * 136];
+    __shared__ float hrow[(kTileH + 6) * kTileW];
+    const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
+                k3 = __uint_as_float(0x3e5d4ae0u);
+    const int tile = blockIdx.x;
+    const int L = find_level_by_tile(g, tile);
+    const LevelGeom lv = g.lv[L];
+    const int t = tile - lv.tileBase;
+    const int x0 = (t % lv.tilesX) * kTileW, y0 = (t / lv.tilesX) * kTileH;
+    const int slot = slot0 + blockIdx.y;
+    const int tid = threadIdx.x;
+    const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
+    uint8_t* out = b.blur + (size_t)slot * g.slotStride + lv.off;
+    // stage tile + 3-px halo with BORDER_REFLECT_101
+    for (int i = tid; i < (kTileH + 6) * (kTileW + 6); i += 256) {
+        int ry = i / (kTileW + 6), rx = i % (kTileW + 6);
+        int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
+        if (gy < 0) gy = -gy;
+        if (gy >= lv.h) gy = 2 * lv.h - 2 - gy;
+        if (gx < 0) gx = -gx;
+        if (gx >= lv.w) gx = 2 * lv.w - 2 - gx;
+        gy = max(0, min(gy, lv.h - 1));
+        gx = max(0, min(gx, lv.w - 1));
+        raw[ry * 136 + rx] = img[(size_t)gy * lv.pitch + gx];
+    }
+    __syncthreads();
+    // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6
+    for (int i = tid; i < (kTileH + 6) * kTileW; i += 256) {
+        int ry = i / kTileW, x = i % kTileW;
+        const uint8_t* p = raw + ry * 136 + x;
+        float s = fmul(k0, (float)p[0]);
+        s = ffma(k1, (float)p[1], s);
+        s = ffma(k2, (float)p[2], s);
+        s = ffma(k3, (float)p[3], s);
+        s = ffma(k2, (float)p[4], s);
+        s = ffma(k1, (float)p[5], s);
+        s = ffma(k0, (float)p[6], s);
+        hrow[i] = s;
+    }
+    __syncthreads();
+    // column pass, 4 pixels per thread
+    for (int i = tid; i < kTileH * (kTileW / 4); i += 256) {
+        int r = i / (kTileW / 4), xq = (i % (kTileW / 4)) * 4;
+        int y = y0 + r;
+        if (y >= lv.h) continue;
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float* h = hrow + (r + 3) * kTileW + xq + k;
+            float s = fmul(k3, h[0]);
+            s = ffma(k2, fadd(h[kTileW], h[-kTileW]), s);
+            s = ffma(k1, fadd(h[2 * kTileW], h[-2 * kTileW]), s);
+            s = ffma(k0, fadd(h[3 * kTileW], h[-3 * kTileW]), s);
+            int v = __float2int_rn(s);
+            v = max(0, min(255, v));
+            word |= (uint32_t)v << (8 * k);
+        }
+        int x = x0 + xq;
+        if (x < lv.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)y * lv.pitch + x) = word;
+    }
+}
+
+// =========================================================================================== A.7 rBRIEF
+__device__ const signed char d_brief_pattern[256][4] = {
+#include "brief_pattern.inc"
+};
+
+__global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot0) {
+    const int slot = slot0 + blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.x * 8 + warp;
+    const int count = b.featCount[slot];
+    if (gi >= count) return;
+    const size_t o = (size_t)slot * g.maxkp + gi;
+    const int L = b.featOctave[o];
+    const LevelGeom lv = g.lv[L];
+    // cv2: centre = (cvRound(pt.x * (1/scale)), cvRound(pt.y * (1/scale))) on the blurred level
+    const float px = b.featPt[o * 2], py = b.featPt[o * 2 + 1];
+    const int cx = __float2int_rn(fmul(px, lv.invScale)), cy = __float2int_rn(fmul(py, lv.invScale));
+    const float ang = fmul(b.featAngle[o], (float)(3.14159265358979323846 / 180.0));
+    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+    const uint8_t* center = b.blur + (size_t)slot * g.slotStride + lv.off + (size_t)cy * lv.pitch + cx;
+    unsigned byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const signed char* pt = d_brief_pattern[lane * 8 + j];
+        float x0f = (float)pt[0], y0f = (float)pt[1], x1f = (float)pt[2], y1f = (float)pt[3];
+        int ix0 = __float2int_rn(fsub(fmul(x0f, ca), fmul(y0f, sa)));
+        int iy0 = __float2int_rn(fadd(fmul(x0f, sa), fmul(y0f, ca)));
+        int ix1 = __float2int_rn(fsub(fmul(x1f, ca), fmul(y1f, sa)));
+        int iy1 = __float2int_rn(fadd(fmul(x1f, sa), fmul(y1f, ca)));
+        int t0 = center[iy0 * lv.pitch + ix0];
+        int t1 = center[iy1 * lv.pitch + ix1];
+        byte |= (unsigned)(t0 < t1) << j;
+    }
+    b.featDesc[o * 32 + lane] = (uint8_t)byte;
+}
+
+// =========================================================================================== launcher
+static long long g_launches = 0;
+long long orb_launch_count() { return g_launches; }
+
+// DVO_DEBUG_SYNC=1: synchronise and report after every kernel (debug only)
+bool debug_sync_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("DVO_DEBUG_SYNC") ? 1 : 0;
+    return v == 1;
+}
+void debug_sync(const char* name, cudaStream_t st) {
+    if (!debug_sync_enabled()) return;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    fprintf(stderr, "[dvo] %-16s %s\n", name, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+}
+
+void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
+                cudaStream_t st) {
+    if (nSlots <= 0) return;
+    cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
+    for (int L = 1; L < g.nlevels; ++L) {
+        dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 7) / 8, nSlots);
+        k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0);
+        ++g_launches;
+        debug_sync("k_pyr_down", st);
+    }
+    {
+        dim3 grid(g.tilesPerFrame, nSlots);
+        if (useTma) k_fast_nms<true><<<grid, 256, 0, st>>>(g, b, *tmaps, slot0);
+        else k_fast_nms<false><<<grid, 256, 0, st>>>(g, b, *tmaps, slot0);
+        ++g_launches;
+        debug_sync("k_fast_nms", st);
+    }
+    k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0);
+    ++g_launches;
+    debug_sync("k_compact", st);
+    k_select<<<dim3(g.nlevels, nSlots), 256, kSelectSmemBytes, st>>>(g, b, slot0);
+    ++g_launches;
+    debug_sync("k_select", st);
+    k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0);
+    ++g_launches;
+    debug_sync("k_angle_pack", st);
+    k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, st>>>(g, b, slot0);
+    ++g_launches;
+    debug_sync("k_blur", st);
+    k_brief<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0);
+    ++g_launches;
+    debug_sync("k_brief", st);
+}
+
+void orb_kernels_init() {
+    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectSmemBytes);
+}
+
+}  // namespace dvo

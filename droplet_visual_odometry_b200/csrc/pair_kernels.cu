@@ -1,0 +1,390 @@
+// Pair-level kernels on sm_100a: brute-force Hamming matching, match ordering, essential-matrix RANSAC, recoverPose.
+// Replaces bf.match + sorted (/root/reference/scripts/visual_odometry_v3.py:219-221), cv.KeyPoint_convert (:355,:358),
+// cv.findEssentialMat (:297-300) and cv.recoverPose (:303-306).  Contract: SURVEY.md Appendix A.8-A.10.
+//
+//   k_nn            A.8  tiled XOR+POPC nearest neighbour (both directions in one launch; 2-NN distance for the ratio test)
+//   k_match_sort    A.8  cross-check / ratio+reverse check, bitonic sort on (distance, queryIdx), point gather, K-normalise
+//   k_solve         A.9  per chunk of 128 RANSAC iterations: cv::RNG sample stream (lane 0) + one 5-point solve per thread
+//   k_score         A.9  Sampson error of every match against every model, warp-reduced inlier counts
+//   k_replay        A.9  cv2's strict-'>' update and adaptive stop rule, replayed in order
+//   k_pose_prep     A.9/A.10  final RANSAC mask, SVD of E -> R1, R2, t
+//   k_cheirality    A.10 per point x 4 candidates DLT triangulation + cheirality votes
+//   k_pose_final    A.10 '>=' cascade, masks, dvo_pose record
+#include "dvo_internal.cuh"
+#include "mathcore.cuh"
+
+namespace dvo {
+void debug_sync(const char* name, cudaStream_t st);
+
+// ransacState layout (ints)
+enum { RS_MAXGOOD = 0, RS_NITERS = 1, RS_DONE = 2, RS_BESTITER = 3, RS_BESTMODEL = 4, RS_RNG_LO = 5, RS_RNG_HI = 6, RS_HASBEST = 7 };
+
+// ================================================================================================ matching
+__global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0) {
+    __shared__ __align__(16) uint32_t tile[128 * 8];
+    const int pi = blockIdx.z;
+    const int dir = blockIdx.y;
+    const int slotA = slotA0 + pi + (dir ? 1 : 0);
+    const int slotB = slotA0 + pi + (dir ? 0 : 1);
+    const int pair = pair0 + pi;
+    const int nA = min(ob.featCount[slotA], pg.maxkp), nB = min(ob.featCount[slotB], pg.maxkp);
+    if (blockIdx.x * 128 >= nA) return;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t* dA = reinterpret_cast<const uint32_t*>(ob.featDesc + (size_t)slotA * og.maxkp * 32);
+    const uint32_t* dB = reinterpret_cast<const uint32_t*>(ob.featDesc + (size_t)slotB * og.maxkp * 32);
+    uint32_t q[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) q[w] = (i < nA) ? dA[(size_t)i * 8 + w] : 0u;
+    int best = 0x7fffffff, bestIdx = -1, second = 0x7fffffff;
+    for (int j0 = 0; j0 < nB; j0 += 128) {
+        __syncthreads();
+        // stage 128 train descriptors: 256 uint4
+        for (int v = threadIdx.x; v < 256; v += 128) {
+            int j = j0 + (v >> 1);
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (j < nB) val = reinterpret_cast<const uint4*>(dB)[(size_t)j * 2 + (v & 1)];
+            reinterpret_cast<uint4*>(tile)[v] = val;
+        }
+        __syncthreads();
+        const int lim = min(128, nB - j0);
+        for (int j = 0; j < lim; ++j) {
+            const uint4 t0 = reinterpret_cast<const uint4*>(tile)[j * 2];
+            const uint4 t1 = reinterpret_cast<const uint4*>(tile)[j * 2 + 1];
+            int d = __popc(q[0] ^ t0.x) + __popc(q[1] ^ t0.y) + __popc(q[2] ^ t0.z) + __popc(q[3] ^ t0.w) +
+                    __popc(q[4] ^ t1.x) + __popc(q[5] ^ t1.y) + __popc(q[6] ^ t1.z) + __popc(q[7] ^ t1.w);
+            if (d < best) { second = best; best = d; bestIdx = j0 + j; }
+            else if (d < second) second = d;
+        }
+    }
+    if (i < nA) {
+        size_t o = ((size_t)pair * 2 + dir) * pg.maxkp + i;
+        pb.nnIdx[o] = bestIdx;
+        pb.nnDist[o] = best;
+        if (dir == 0) pb.nn2Dist[(size_t)pair * pg.maxkp + i] = second;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0,
+                                                     double fx, double fy, double cx, double cy) {
+    extern __shared__ uint32_t keys[];
+    __shared__ int s_count;
+    const int pi = blockIdx.x;
+    const int pair = pair0 + pi;
+    const int slotA = slotA0 + pi, slotB = slotA + 1;
+    const int nA = min(ob.featCount[slotA], pg.maxkp), nB = min(ob.featCount[slotB], pg.maxkp);
+    const int tid = threadIdx.x;
+    const int* fwd = pb.nnIdx + ((size_t)pair * 2 + 0) * pg.maxkp;
+    const int* fwdD = pb.nnDist + ((size_t)pair * 2 + 0) * pg.maxkp;
+    const int* bwd = pb.nnIdx + ((size_t)pair * 2 + 1) * pg.maxkp;
+    const int* d2 = pb.nn2Dist + (size_t)pair * pg.maxkp;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < pg.sortCap; i += 1024) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < nA && nB > 0) {
+            int j = fwd[i];
+            bool ok = j >= 0 && bwd[j] == i;
+            if (pg.matcher == DVO_MATCH_KNN_RATIO) {
+                // knnMatch returns < 2 neighbours when the train set has one descriptor: the reference's unpacking needs two
+                ok = ok && nB >= 2 && ((double)fwdD[i] < (double)pg.ratio * (double)d2[i]);
+            }
+            if (ok) { key = ((uint32_t)fwdD[i] << 16) | (uint32_t)i; ++local; }
+        }
+        keys[i] = key;
+    }
+    atomicAdd(&s_count, local);
+    __syncthreads();
+    // bitonic sort ascending
+    for (int k = 2; k <= pg.sortCap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < pg.sortCap; i += 1024) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int M = s_count;
+    if (tid == 0) pb.matchCount[pair] = M;
+    const float* ptA = ob.featPt + (size_t)slotA * og.maxkp * 2;
+    const float* ptB = ob.featPt + (size_t)slotB * og.maxkp * 2;
+    const size_t o = (size_t)pair * pg.maxkp;
+    for (int r = tid; r < M; r += 1024) {
+        uint32_t key = keys[r];
+        int i = key & 0xFFFF, d = key >> 16, j = fwd[i];
+        pb.matches[(o + r) * 3 + 0] = i;
+        pb.matches[(o + r) * 3 + 1] = j;
+        pb.matches[(o + r) * 3 + 2] = d;
+        float ax = ptA[i * 2], ay = ptA[i * 2 + 1], bx = ptB[j * 2], by = ptB[j * 2 + 1];
+        pb.ptsPrev[(o + r) * 2] = ax; pb.ptsPrev[(o + r) * 2 + 1] = ay;
+        pb.ptsCur[(o + r) * 2] = bx; pb.ptsCur[(o + r) * 2 + 1] = by;
+        double* np_ = pb.normPts + (o + r) * 4;
+        np_[0] = ((double)ax - cx) / fx; np_[1] = ((double)ay - cy) / fy;
+        np_[2] = ((double)bx - cx) / fx; np_[3] = ((double)by - cy) / fy;
+    }
+    if (tid == 0) {
+        int* rs = pb.ransacState + pair * 8;
+        rs[RS_MAXGOOD] = 0;
+        rs[RS_NITERS] = pg.maxIters;
+        rs[RS_DONE] = (M <= 5) ? 1 : 0;      // < 5: no model; == 5: cv2 returns the stacked minimal solutions (not a 3x3 E)
+        rs[RS_BESTITER] = -1;
+        rs[RS_BESTMODEL] = -1;
+        rs[RS_RNG_LO] = (int)0xFFFFFFFFu;
+        rs[RS_RNG_HI] = (int)0xFFFFFFFFu;
+        rs[RS_HASBEST] = 0;
+    }
+}
+
+// ================================================================================================ RANSAC
+__global__ void __launch_bounds__(kRansacChunk) k_solve(PairGeom pg, PairBuffers pb, int pair0, int chunk) {
+    __shared__ int s_samples[kRansacChunk][5];
+    const int pair = pair0 + blockIdx.x;
+    int* rs = pb.ransacState + pair * 8;
+    if (rs[RS_DONE]) return;
+    const int M = pb.matchCount[pair];
+    const int it0 = chunk * kRansacChunk;
+    const int nIt = min(kRansacChunk, pg.maxIters - it0);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        // cv::RNG stream, 5 distinct positions per iteration with single-index redraw (getSubset)
+        uint64_t state = ((uint64_t)(uint32_t)rs[RS_RNG_HI] << 32) | (uint32_t)rs[RS_RNG_LO];
+        for (int it = 0; it < nIt; ++it) {
+            int idx[5];
+            int i = 0;
+            while (i < 5) {
+                int v = (int)(cvrng_next(state) % (uint32_t)M);
+                bool dup = false;
+                for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
+                if (dup) continue;
+                idx[i++] = v;
+            }
+            for (int k = 0; k < 5; ++k) s_samples[it][k] = idx[k];
+        }
+        rs[RS_RNG_LO] = (int)(uint32_t)state;
+        rs[RS_RNG_HI] = (int)(uint32_t)(state >> 32);
+    }
+    __syncthreads();
+    if (tid >= nIt) return;
+    const double* np_ = pb.normPts + (size_t)pair * pg.maxkp * 4;
+    double x1[10], x2[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double* p = np_ + (size_t)s_samples[tid][k] * 4;
+        x1[2 * k] = p[0]; x1[2 * k + 1] = p[1];
+        x2[2 * k] = p[2]; x2[2 * k + 1] = p[3];
+        pb.samples[((size_t)pair * pg.maxIters + it0 + tid) * 5 + k] = s_samples[tid][k];
+    }
+    double* models = pb.models + ((size_t)pair * kRansacChunk + tid) * kMaxModels * 9;
+    int n = five_point_solve(x1, x2, models);
+    pb.modelCount[(size_t)pair * kRansacChunk + tid] = n;
+}
+
+__global__ void __launch_bounds__(256) k_score(PairGeom pg, PairBuffers pb, int pair0, int chunk, float t32) {
+    const int pair = pair0 + blockIdx.y;
+    const int* rs = pb.ransacState + pair * 8;
+    if (rs[RS_DONE]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + warp;         // (iteration-in-chunk, model)
+    const int it = slot / kMaxModels, k = slot % kMaxModels;
+    if (it >= kRansacChunk) return;
+    const int itAbs = chunk * kRansacChunk + it;
+    if (itAbs >= rs[RS_NITERS] || itAbs >= pg.maxIters) return;
+    if (k >= pb.modelCount[(size_t)pair * kRansacChunk + it]) return;
+    const double* Eg = pb.models + (((size_t)pair * kRansacChunk + it) * kMaxModels + k) * 9;
+    double E[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) E[j] = Eg[j];
+    const int M = pb.matchCount[pair];
+    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+    int good = 0;
+    for (int i = lane; i < M; i += 32) {
+        double4 p = np4[i];
+        float err = sampson_error_f32(E, p.x, p.y, p.z, p.w);
+        good += (err <= t32) ? 1 : 0;
+    }
+    good = __reduce_add_sync(0xffffffffu, good);
+    if (lane == 0) pb.modelGood[((size_t)pair * kRansacChunk + it) * kMaxModels + k] = good;
+}
+
+__global__ void k_replay(PairGeom pg, PairBuffers pb, int pair0, int nPairs, int chunk) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= nPairs) return;
+    const int pair = pair0 + pi;
+    int* rs = pb.ransacState + pair * 8;
+    if (rs[RS_DONE]) return;
+    const int M = pb.matchCount[pair];
+    int maxGood = rs[RS_MAXGOOD], niters = rs[RS_NITERS];
+    const int it0 = chunk * kRansacChunk;
+    const int itEnd = min(it0 + kRansacChunk, pg.maxIters);
+    int it = it0;
+    for (; it < itEnd; ++it) {
+        if (it >= niters) break;
+        const int nm = pb.modelCount[(size_t)pair * kRansacChunk + (it - it0)];
+        for (int k = 0; k < nm; ++k) {
+            int good = pb.modelGood[((size_t)pair * kRansacChunk + (it - it0)) * kMaxModels + k];
+            if (good > max(maxGood, 4)) {
+                maxGood = good;
+                const double* Eg = pb.models + (((size_t)pair * kRansacChunk + (it - it0)) * kMaxModels + k) * 9;
+                for (int j = 0; j < 9; ++j) pb.bestE[pair * 9 + j] = Eg[j];
+                rs[RS_BESTITER] = it;
+                rs[RS_BESTMODEL] = k;
+                rs[RS_HASBEST] = 1;
+                niters = ransac_update_num_iters(pg.prob, (double)(M - good) / M, 5, niters);
+            }
+        }
+    }
+    rs[RS_MAXGOOD] = maxGood;
+    rs[RS_NITERS] = niters;
+    if (it >= niters || it >= pg.maxIters) rs[RS_DONE] = 1;
+}
+
+// ================================================================================================ recoverPose
+__global__ void __launch_bounds__(256) k_pose_prep(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
+    __shared__ int s_cnt;
+    const int pi = blockIdx.x, pair = pair0 + pi;
+    const int* rs = pb.ransacState + pair * 8;
+    const int M = pb.matchCount[pair];
+    PoseScratch& sc = ps[pair];
+    if (threadIdx.x == 0) { s_cnt = 0; for (int k = 0; k < 4; ++k) sc.good[k] = 0; }
+    __syncthreads();
+    uint8_t* mask = pb.ransacMask + (size_t)pair * pg.maxkp;
+    if (!rs[RS_HASBEST]) {
+        for (int i = threadIdx.x; i < M; i += 256) mask[i] = 0;
+        if (threadIdx.x == 0) sc.nInl = 0;
+        return;
+    }
+    double E[9];
+    for (int j = 0; j < 9; ++j) E[j] = pb.bestE[pair * 9 + j];
+    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+    int local = 0;
+    for (int i = threadIdx.x; i < M; i += 256) {
+        double4 p = np4[i];
+        int in = sampson_error_f32(E, p.x, p.y, p.z, p.w) <= t32 ? 1 : 0;
+        mask[i] = (uint8_t)in;
+        local += in;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc.nInl = s_cnt;
+        decompose_essential(E, sc.R1, sc.R2, sc.t);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cheirality(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0) {
+    const int pi = blockIdx.y, pair = pair0 + pi;
+    const int* rs = pb.ransacState + pair * 8;
+    if (!rs[RS_HASBEST]) return;
+    const int M = pb.matchCount[pair];
+    if (blockIdx.x * 128 >= M) return;
+    PoseScratch& sc = ps[pair];
+    __shared__ double sR1[9], sR2[9], st[3], snt[3];
+    if (threadIdx.x < 9) { sR1[threadIdx.x] = sc.R1[threadIdx.x]; sR2[threadIdx.x] = sc.R2[threadIdx.x]; }
+    if (threadIdx.x < 3) { st[threadIdx.x] = sc.t[threadIdx.x]; snt[threadIdx.x] = -sc.t[threadIdx.x]; }
+    __syncthreads();
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    int flags = 0;
+    if (i < M) {
+        const double* p = pb.normPts + ((size_t)pair * pg.maxkp + i) * 4;
+        double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+        flags |= cheirality_ok(sR1, st, x1, y1, x2, y2, pg.distThresh) ? 1 : 0;
+        flags |= cheirality_ok(sR2, st, x1, y1, x2, y2, pg.distThresh) ? 2 : 0;
+        flags |= cheirality_ok(sR1, snt, x1, y1, x2, y2, pg.distThresh) ? 4 : 0;
+        flags |= cheirality_ok(sR2, snt, x1, y1, x2, y2, pg.distThresh) ? 8 : 0;
+        pb.poseMask[(size_t)pair * pg.maxkp + i] = (uint8_t)flags;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int c = __reduce_add_sync(0xffffffffu, (flags >> k) & 1);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sc.good[k], c);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pose_final(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, PoseScratch* ps, int slotA0,
+                                                    int pair0) {
+    const int pi = blockIdx.x, pair = pair0 + pi;
+    const int* rs = pb.ransacState + pair * 8;
+    const int M = pb.matchCount[pair];
+    const PoseScratch& sc = ps[pair];
+    dvo_pose& out = pb.poses[pair];
+    uint8_t* pm = pb.poseMask + (size_t)pair * pg.maxkp;
+    int k = 0;
+    if (rs[RS_HASBEST]) {
+        const int g0 = sc.good[0], g1 = sc.good[1], g2 = sc.good[2], g3 = sc.good[3];
+        if (g0 >= g1 && g0 >= g2 && g0 >= g3) k = 0;
+        else if (g1 >= g0 && g1 >= g2 && g1 >= g3) k = 1;
+        else if (g2 >= g0 && g2 >= g1 && g2 >= g3) k = 2;
+        else k = 3;
+        for (int i = threadIdx.x; i < M; i += 256) pm[i] = ((pm[i] >> k) & 1) ? 255 : 0;
+    } else {
+        for (int i = threadIdx.x; i < M; i += 256) pm[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        out.n_matches = M;
+        out.n_prev = ob.featCount[slotA0 + pi];
+        out.n_cur = ob.featCount[slotA0 + pi + 1];
+        out.ransac_iters = rs[RS_NITERS];
+        out.best_iter = rs[RS_BESTITER];
+        out.reserved = rs[RS_BESTMODEL];
+        if (!rs[RS_HASBEST]) {
+            out.status = (M < 5) ? DVO_PAIR_TOO_FEW_MATCHES : DVO_PAIR_NO_MODEL;
+            for (int j = 0; j < 9; ++j) { out.R[j] = (j % 4 == 0) ? 1.0 : 0.0; out.E[j] = 0.0; }
+            out.t[0] = out.t[1] = out.t[2] = 0.0;
+            out.n_inliers = 0; out.n_good = 0; out.candidate = -1;
+        } else {
+            out.status = DVO_PAIR_OK;
+            const double* R = (k & 1) ? sc.R2 : sc.R1;
+            const double sgn = (k & 2) ? -1.0 : 1.0;
+            for (int j = 0; j < 9; ++j) { out.R[j] = R[j]; out.E[j] = pb.bestE[pair * 9 + j]; }
+            for (int j = 0; j < 3; ++j) out.t[j] = sgn * sc.t[j];
+            out.n_inliers = sc.nInl;
+            out.n_good = sc.good[k];
+            out.candidate = k;
+        }
+    }
+}
+
+// ================================================================================================ launcher
+static long long g_pair_launches = 0;
+long long pair_launch_count() { return g_pair_launches; }
+
+void pair_kernels_init(int sortBytes) {
+    if (sortBytes > 48 * 1024) cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortBytes);
+}
+
+void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+                  int nPairs, const double* K, cudaStream_t st) {
+    if (nPairs <= 0) return;
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double thr = pg.threshold / ((fx + fy) / 2.0);
+    const float t32 = (float)(thr * thr);
+    PoseScratch* ps = pb.poseScratch;
+    k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+    k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy);
+    g_pair_launches += 2;
+    debug_sync("k_nn+sort", st);
+    for (int c = 0; c < pg.nChunks; ++c) {
+        k_solve<<<nPairs, kRansacChunk, 0, st>>>(pg, pb, pair0, c);
+        debug_sync("k_solve", st);
+        k_score<<<dim3(kRansacChunk * kMaxModels / 8, nPairs), 256, 0, st>>>(pg, pb, pair0, c, t32);
+        debug_sync("k_score", st);
+        k_replay<<<(nPairs + 63) / 64, 64, 0, st>>>(pg, pb, pair0, nPairs, c);
+        g_pair_launches += 3;
+        debug_sync("k_replay", st);
+    }
+    k_pose_prep<<<nPairs, 256, 0, st>>>(pg, pb, ps, pair0, t32);
+    debug_sync("k_pose_prep", st);
+    k_cheirality<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(pg, pb, ps, pair0);
+    debug_sync("k_cheirality", st);
+    k_pose_final<<<nPairs, 256, 0, st>>>(og, ob, pg, pb, ps, slotA0, pair0);
+    g_pair_launches += 3;
+    debug_sync("k_pose_final", st);
+}
+
+}  // namespace dvo

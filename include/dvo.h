@@ -1,0 +1,145 @@
+/* libdvo -- C ABI of the B200-native visual-odometry hot path.
+ *
+ * Drop-in boundary for the per-frame-pair chain of theivyzhang/droplet_visual_odometry.  The reference has no FFI: its
+ * hot path is five cv2 calls made from Python (scripts/visual_odometry_v3.py).  Each entry point below names the
+ * reference call(s) it replaces; the Python host side (droplet_visual_odometry_b200/visual_odometry_v3.py) binds
+ * them with ctypes and keeps the reference's class and method names.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - return 0 on success, a negative DVO_E_* code on error; dvo_last_error(ctx) gives the message.  No exceptions
+ *     cross this boundary.  Per-pair soft failures (too few matches, no model) are reported in dvo_pose.status.
+ *   - "d_" pointers are device memory owned by the caller (torch tensors on the Python side); "h_" are host pointers.
+ *     The library never frees caller memory.  Variable-length outputs are written up to the given capacity and the
+ *     true count returned; a count above capacity fails with DVO_E_CAPACITY.
+ *   - a context is bound to one device, is not thread-safe, and enqueues all work on the given stream; calls are
+ *     asynchronous unless their name ends in _host or says they synchronise.
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef DVO_H_
+#define DVO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVO_OK 0
+#define DVO_E_INVALID (-1)     /* bad argument */
+#define DVO_E_CUDA (-2)        /* CUDA runtime / driver error */
+#define DVO_E_CAPACITY (-3)    /* caller buffer or context capacity too small */
+#define DVO_E_NODEVICE (-4)    /* no usable CUDA device */
+
+#define DVO_MATCH_CROSSCHECK 0 /* cv.BFMatcher(NORM_HAMMING, crossCheck=True).match   (visual_odometry_v3.py:75,219) */
+#define DVO_MATCH_KNN_RATIO 1  /* knnMatch(k=2) + 0.75 ratio (:203,:227) + reverse 1-NN check (BASELINE config 4)   */
+
+/* per-pair status */
+#define DVO_PAIR_OK 0
+#define DVO_PAIR_TOO_FEW_MATCHES 1 /* < 5 correspondences: cv.findEssentialMat returns None */
+#define DVO_PAIR_NO_MODEL 2        /* RANSAC found no model with > 4 inliers                */
+
+typedef struct dvo_ctx dvo_ctx;
+
+typedef struct dvo_config {
+    int width, height;       /* frame size in pixels, each <= 4096                                         */
+    int nfeatures;           /* cv.ORB_create(nfeatures=...)   reference literal: 500 (visual_odometry_v3.py:96) */
+    int nlevels;             /* ORB pyramid levels, 1..8 (cv2 default 8)                                    */
+    int fast_threshold;      /* cv2 default 20                                                             */
+    int max_frames;          /* frame slots resident at once (batch size + 1 for the sequence runner)      */
+    int matcher;             /* DVO_MATCH_*                                                                */
+    int ransac_max_iters;    /* cv.findEssentialMat maxIters, cv2 default 1000                             */
+    double ransac_prob;      /* 0.999  (visual_odometry_v3.py:300)                                         */
+    double ransac_threshold; /* 1.0 px (visual_odometry_v3.py:300)                                         */
+    double distance_thresh;  /* cv.recoverPose distanceThresh, cv2 default 50                              */
+    float ratio;             /* 0.75   (visual_odometry_v3.py:227)                                         */
+    int use_tma;             /* 1: stage FAST tiles with TMA (default); 0: plain loads (debug)             */
+} dvo_config;
+
+/* Result of one frame pair: what cv.findEssentialMat + cv.recoverPose return (visual_odometry_v3.py:297-306). */
+typedef struct dvo_pose {
+    double R[9];             /* recoverPose rotation, row-major             */
+    double t[3];             /* recoverPose translation (unit norm)         */
+    double E[9];             /* findEssentialMat result, row-major          */
+    int32_t status;          /* DVO_PAIR_*                                  */
+    int32_t n_matches;       /* correspondences fed to findEssentialMat     */
+    int32_t n_inliers;       /* RANSAC mask population                      */
+    int32_t n_good;          /* recoverPose return value (cheirality count) */
+    int32_t ransac_iters;    /* iterations cv2's loop would have executed   */
+    int32_t best_iter;       /* iteration that produced E                   */
+    int32_t candidate;       /* 0..3: which (R1|R2, +-t) recoverPose chose   */
+    int32_t n_prev, n_cur;   /* keypoints in the two frames                 */
+    int32_t reserved;
+} dvo_pose;
+
+/* Device-side views of one frame's features: cv2 detectAndCompute output (visual_odometry_v3.py:373). */
+typedef struct dvo_features {
+    float* d_pt;        /* [cap][2] KeyPoint.pt                 */
+    float* d_size;      /* [cap]    KeyPoint.size               */
+    float* d_angle;     /* [cap]    KeyPoint.angle (degrees)    */
+    float* d_response;  /* [cap]    KeyPoint.response (Harris)  */
+    int32_t* d_octave;  /* [cap]    KeyPoint.octave             */
+    uint8_t* d_desc;    /* [cap][32] descriptors                */
+    int32_t* d_count;   /* [1]      number of keypoints         */
+    int32_t capacity;
+} dvo_features;
+
+/* Device-side views of one pair's correspondences and masks. */
+typedef struct dvo_pair_arrays {
+    int32_t* d_matches;  /* [cap][3] (queryIdx, trainIdx, distance), order = sorted(bf.match(...), key=distance) */
+    float* d_pts_prev;   /* [cap][2] cv.KeyPoint_convert of the previous-frame keypoints (visual_odometry_v3.py:355) */
+    float* d_pts_cur;    /* [cap][2]                                                         (:358) */
+    uint8_t* d_ransac_mask; /* [cap] findEssentialMat mask (0/1)   */
+    uint8_t* d_pose_mask;   /* [cap] recoverPose mask (0/255)       */
+    int32_t capacity;
+} dvo_pair_arrays;
+
+void dvo_default_config(dvo_config* cfg);
+int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out);
+void dvo_destroy(dvo_ctx* ctx);
+const char* dvo_last_error(const dvo_ctx* ctx);
+const char* dvo_version(void);
+int dvo_max_keypoints(const dvo_ctx* ctx);   /* capacity needed for dvo_features / dvo_pair_arrays */
+int dvo_max_frames(const dvo_ctx* ctx);
+long long dvo_kernel_launches(const dvo_ctx* ctx);   /* kernels launched by this context so far */
+
+/* Upload n frames (device or host memory, row pitch `pitch`, `frame_stride` bytes apart) into slots
+ * [slot0, slot0+n).  kind: 0 = source is device memory, 1 = source is (preferably pinned) host memory. */
+int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, size_t frame_stride, int slot0, int kind,
+                    void* stream);
+
+/* ORB detect+describe on slots [slot0, slot0+n): replaces feature_detector.detectAndCompute
+ * (visual_odometry_v3.py:373, called from compute_current_image_elements :370-379). */
+int dvo_orb(dvo_ctx* ctx, int slot0, int n, void* stream);
+
+/* Copy one slot's features into caller device buffers (async on stream). */
+int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stream);
+
+/* Match + pose for pairs (slot0+i, slot0+i+1), i < n, results in pair slots [pair0, pair0+n): replaces bf.match +
+ * sorted (:219-221), cv.KeyPoint_convert (:355,:358), cv.findEssentialMat (:297-300), cv.recoverPose (:303-306).
+ * K is the 3x3 row-major camera matrix (host pointer, read before the call returns). */
+int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream);
+
+/* Copy n pair results (device->device or device->host, async on stream). kind: 0 device dst, 1 host dst. */
+int dvo_get_poses(dvo_ctx* ctx, int pair0, int n, dvo_pose* dst, int kind, void* stream);
+int dvo_get_pair_arrays(dvo_ctx* ctx, int pair, const dvo_pair_arrays* out, void* stream);
+
+/* Whole-sequence runner: consecutive-pair VO over n_frames frames; writes n_frames-1 dvo_pose records.
+ * Frames are processed in batches of max_frames-1 with a one-frame carry, each frame's ORB computed once.
+ * kind: 0 = frames and poses in device memory (async), 1 = host memory (H2D/D2H inside; synchronises). */
+int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride, const double* K,
+                 dvo_pose* poses, int kind, void* stream);
+
+/* Stage taps for the parity tests (device destination, tightly packed rows of `w` bytes unless noted). */
+int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota);
+int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which /*0 pyramid, 1 blurred, 2 nms score map*/,
+                  uint8_t* d_dst, void* stream);
+int dvo_tap_candidates(dvo_ctx* ctx, int slot, int level, uint32_t* d_dst /*packed score<<24|y<<12|x*/, int capacity,
+                       int* h_count /*host, synchronises*/, void* stream);
+int dvo_tap_ransac(dvo_ctx* ctx, int pair, int32_t* h_state8 /*host, synchronises*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVO_H_ */
