@@ -74,6 +74,8 @@ def load_library():
     lib.dvo_orb.argtypes = [vp, ci, ci, vp]
     lib.dvo_get_features.argtypes = [vp, ci, ctypes.POINTER(dvo_features), vp]
     lib.dvo_pairs.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_set_features.argtypes = [vp, ci, vp, vp, ci, ci, vp]
+    lib.dvo_pose_points.argtypes = [vp, ci, vp, vp, ci, vp, ci, vp]
     lib.dvo_get_poses.argtypes = [vp, ci, ci, vp, ci, vp]
     lib.dvo_get_pair_arrays.argtypes = [vp, ci, ctypes.POINTER(dvo_pair_arrays), vp]
     lib.dvo_sequence.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, vp]
@@ -193,6 +195,31 @@ class Context:
     def pairs(self, slot0, pair0, n, K):
         Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
         self._check(self.lib.dvo_pairs(self._h, slot0, pair0, n, Kc.ctypes.data, self._stream()), "dvo_pairs")
+
+    def set_features(self, slot, pt, desc):
+        """Overwrite a slot with caller keypoint coordinates (n,2) f32 and descriptors (n,32) u8 (host arrays)."""
+        pt = np.ascontiguousarray(pt, dtype=np.float32).reshape(-1, 2)
+        desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        assert len(pt) == len(desc)
+        self._check(self.lib.dvo_set_features(self._h, slot, pt.ctypes.data, desc.ctypes.data, len(pt), 1, self._stream()),
+                    "dvo_set_features")
+
+    def pose_points(self, p_prev, p_cur, K, pair=0):
+        """findEssentialMat + recoverPose on caller correspondences (host (n,2) arrays or cuda float32 tensors)."""
+        t = self.torch
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        if isinstance(p_prev, np.ndarray) or not hasattr(p_prev, "is_cuda"):
+            a = np.ascontiguousarray(p_prev, dtype=np.float32).reshape(-1, 2)
+            b = np.ascontiguousarray(p_cur, dtype=np.float32).reshape(-1, 2)
+            self._check(self.lib.dvo_pose_points(self._h, pair, a.ctypes.data, b.ctypes.data, len(a), Kc.ctypes.data, 1,
+                                                 self._stream()), "dvo_pose_points")
+            self.sync()
+            return len(a)
+        a = p_prev.contiguous().to(t.float32)
+        b = p_cur.contiguous().to(t.float32)
+        self._check(self.lib.dvo_pose_points(self._h, pair, a.data_ptr(), b.data_ptr(), a.shape[0], Kc.ctypes.data, 0,
+                                             self._stream()), "dvo_pose_points")
+        return a.shape[0]
 
     def poses(self, pair0, n):
         out = np.zeros(n, dtype=POSE_DTYPE)

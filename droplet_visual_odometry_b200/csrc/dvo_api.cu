@@ -171,6 +171,16 @@ extern "C" {
 
 const char* dvo_version(void) { return "libdvo 0.1 (sm_100a)"; }
 
+int dvo_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(dvo_config);
+        case 1: return (int)sizeof(dvo_pose);
+        case 2: return (int)sizeof(dvo_features);
+        case 3: return (int)sizeof(dvo_pair_arrays);
+        default: return DVO_E_INVALID;
+    }
+}
+
 void dvo_default_config(dvo_config* c) {
     memset(c, 0, sizeof *c);
     c->width = 1280; c->height = 1024;
@@ -185,7 +195,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     if (!cfg || !out) return DVO_E_INVALID;
     *out = nullptr;
     if (cfg->width < 64 || cfg->height < 64 || cfg->width > kMaxImageDim || cfg->height > kMaxImageDim ||
-        cfg->nlevels < 1 || cfg->nlevels > kMaxLevels || cfg->nfeatures < 1 || cfg->nfeatures > 30000 || cfg->max_frames < 2 ||
+        cfg->nlevels < 1 || cfg->nlevels > kMaxLevels || cfg->nfeatures < 1 || cfg->nfeatures > 65000 || cfg->max_frames < 2 ||
         cfg->ransac_max_iters < 1)
         return DVO_E_INVALID;
     int ndev = 0;
@@ -394,7 +404,43 @@ int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* 
         return DVO_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->pg.sortCap * sizeof(uint32_t) > 200 * 1024) {
+        ctx->err = "dvo_pairs: nfeatures too large for the in-shared-memory match sort (max ~49000 keypoints)";
+        return DVO_E_CAPACITY;
+    }
     launch_pairs(ctx->og, ctx->ob, ctx->pg, ctx->pb, slot0, pair0, n, K, st);
+    CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+int dvo_set_features(dvo_ctx* ctx, int slot, const float* pt, const uint8_t* desc, int n, int kind, void* stream) {
+    if (!ctx || slot < 0 || slot >= ctx->nSlots || n < 0 || (n > 0 && (!pt || !desc))) return DVO_E_INVALID;
+    if (n > ctx->og.maxkp) { ctx->err = "dvo_set_features: n exceeds dvo_max_keypoints"; return DVO_E_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t o = (size_t)slot * ctx->og.maxkp;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->ob.featPt + o * 2, pt, sizeof(float) * 2 * n, k, st));
+        CK(cudaMemcpyAsync(ctx->ob.featDesc + o * 32, desc, 32 * (size_t)n, k, st));
+    }
+    CK(cudaMemcpyAsync(ctx->ob.featCount + slot, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // &n is a stack variable
+    return DVO_OK;
+}
+
+int dvo_pose_points(dvo_ctx* ctx, int pair, const float* pts_prev, const float* pts_cur, int n, const double* K, int kind,
+                    void* stream) {
+    if (!ctx || !K || pair < 0 || pair >= ctx->nPairs || n < 0 || (n > 0 && (!pts_prev || !pts_cur))) return DVO_E_INVALID;
+    if (n > ctx->og.maxkp) { ctx->err = "dvo_pose_points: n exceeds dvo_max_keypoints"; return DVO_E_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t o = (size_t)pair * ctx->og.maxkp;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->pb.ptsPrev + o * 2, pts_prev, sizeof(float) * 2 * n, k, st));
+        CK(cudaMemcpyAsync(ctx->pb.ptsCur + o * 2, pts_cur, sizeof(float) * 2 * n, k, st));
+    }
+    launch_points_prep(ctx->pg, ctx->pb, pair, n, K, st);
+    launch_ransac_pose(ctx->og, ctx->ob, ctx->pg, ctx->pb, -1, pair, 1, K, st);
     CK(cudaGetLastError());
     return DVO_OK;
 }

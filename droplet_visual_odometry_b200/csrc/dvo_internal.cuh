@@ -120,4 +120,8 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
 void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
                   int pair0, int nPairs, const double* K, cudaStream_t st);
 
+void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
+                        int pair0, int nPairs, const double* K, cudaStream_t st);
+void launch_points_prep(const PairGeom& pg, const PairBuffers& pb, int pair, int n, const double* K, cudaStream_t st);
+
 }  // namespace dvo

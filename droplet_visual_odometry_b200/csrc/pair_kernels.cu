@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(256) k_pose_final(OrbGeom og, OrbBuffers ob, P
     }
     if (threadIdx.x == 0) {
         out.n_matches = M;
-        out.n_prev = ob.featCount[slotA0 + pi];
-        out.n_cur = ob.featCount[slotA0 + pi + 1];
+        out.n_prev = slotA0 >= 0 ? ob.featCount[slotA0 + pi] : M;
+        out.n_cur = slotA0 >= 0 ? ob.featCount[slotA0 + pi + 1] : M;
         out.ransac_iters = rs[RS_NITERS];
         out.best_iter = rs[RS_BESTITER];
         out.reserved = rs[RS_BESTMODEL];
@@ -355,20 +355,44 @@ static long long g_pair_launches = 0;
 long long pair_launch_count() { return g_pair_launches; }
 
 void pair_kernels_init(int sortBytes) {
-    if (sortBytes > 48 * 1024) cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortBytes);
+    // contexts too large for the in-smem sort (points-only use) never launch k_match_sort: dvo_pairs refuses them
+    if (sortBytes > 48 * 1024 && sortBytes <= 200 * 1024)
+        cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortBytes);
 }
 
-void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
-                  int nPairs, const double* K, cudaStream_t st) {
+// Points-only entry: normalise caller correspondences and reset the RANSAC state (no matching stage).
+__global__ void __launch_bounds__(256) k_points_prep(PairGeom pg, PairBuffers pb, int pair, int n, double fx, double fy, double cx,
+                                                     double cy) {
+    const size_t o = (size_t)pair * pg.maxkp;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        float ax = pb.ptsPrev[(o + r) * 2], ay = pb.ptsPrev[(o + r) * 2 + 1];
+        float bx = pb.ptsCur[(o + r) * 2], by = pb.ptsCur[(o + r) * 2 + 1];
+        double* np_ = pb.normPts + (o + r) * 4;
+        np_[0] = ((double)ax - cx) / fx; np_[1] = ((double)ay - cy) / fy;
+        np_[2] = ((double)bx - cx) / fx; np_[3] = ((double)by - cy) / fy;
+        pb.matches[(o + r) * 3 + 0] = r; pb.matches[(o + r) * 3 + 1] = r; pb.matches[(o + r) * 3 + 2] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        pb.matchCount[pair] = n;
+        int* rs = pb.ransacState + pair * 8;
+        rs[RS_MAXGOOD] = 0; rs[RS_NITERS] = pg.maxIters; rs[RS_DONE] = (n <= 5) ? 1 : 0;
+        rs[RS_BESTITER] = -1; rs[RS_BESTMODEL] = -1;
+        rs[RS_RNG_LO] = (int)0xFFFFFFFFu; rs[RS_RNG_HI] = (int)0xFFFFFFFFu; rs[RS_HASBEST] = 0;
+    }
+}
+
+void launch_points_prep(const PairGeom& pg, const PairBuffers& pb, int pair, int n, const double* K, cudaStream_t st) {
+    k_points_prep<<<64, 256, 0, st>>>(pg, pb, pair, n, K[0], K[4], K[2], K[5]);
+    g_pair_launches += 1;
+}
+
+void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+                        int nPairs, const double* K, cudaStream_t st) {
     if (nPairs <= 0) return;
-    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double fx = K[0], fy = K[4];
     const double thr = pg.threshold / ((fx + fy) / 2.0);
     const float t32 = (float)(thr * thr);
     PoseScratch* ps = pb.poseScratch;
-    k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
-    k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy);
-    g_pair_launches += 2;
-    debug_sync("k_nn+sort", st);
     for (int c = 0; c < pg.nChunks; ++c) {
         k_solve<<<nPairs, kRansacChunk, 0, st>>>(pg, pb, pair0, c);
         debug_sync("k_solve", st);
@@ -385,6 +409,17 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
     k_pose_final<<<nPairs, 256, 0, st>>>(og, ob, pg, pb, ps, slotA0, pair0);
     g_pair_launches += 3;
     debug_sync("k_pose_final", st);
+}
+
+void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+                  int nPairs, const double* K, cudaStream_t st) {
+    if (nPairs <= 0) return;
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+    k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy);
+    g_pair_launches += 2;
+    debug_sync("k_nn+sort", st);
+    launch_ransac_pose(og, ob, pg, pb, slotA0, pair0, nPairs, K, st);
 }
 
 }  // namespace dvo

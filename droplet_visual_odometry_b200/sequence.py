@@ -1,0 +1,160 @@
+"""Sequence-level host logic: consecutive-pair VO over an offline sequence, sharded by frame pair across GPUs, chained
+into a trajectory and written in the reference's stamped text formats.
+
+Reference flow being replaced (ROS-free): ``UnitTestingExtractData.compute_all_gt_vo_comparison_list``
+(/root/reference/scripts/trajectory_evaluation_dual_process.py:170-252) calls ``visual_odometry_calculations`` once per
+consecutive pair, sequentially, chains ``cur = prev.dot(rel)`` (visual_odometry_v3.py:367) and finally writes
+``stamped_traj_estimate_{absolute,relative,velocity}.txt`` (:280-290, :307-309).
+
+Here pairs are independent units: rank r of G processes a contiguous block of pairs (one-frame halo), one NCCL
+all-gather of the fixed-size per-pair records (R, t, status ...: 208 bytes) follows, and every rank chains the
+4x4 products.  No other collective exists on this path.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import pose_estimation_module as PEM
+from . import transformations_lite as transf
+from ._native import POSE_DTYPE, PAIR_OK
+
+
+# ------------------------------------------------------------------------------------------------ partitioning
+def shard_pairs(n_pairs: int, world_size: int, rank: int):
+    """Contiguous block [start, end) of pair indices for ``rank``: ceil(n/G) pairs per rank, last ranks may be short or
+    empty.  Pair i uses frames i and i+1, so the rank touches frames [start, end]."""
+    per = (n_pairs + world_size - 1) // world_size if world_size > 0 else n_pairs
+    start = min(rank * per, n_pairs)
+    end = min(start + per, n_pairs)
+    return start, end
+
+
+# ------------------------------------------------------------------------------------------------ pose algebra (host, a12)
+def relative_transform(R, t, scale: float = 1.0, exact_rotation: bool = False):
+    """4x4 of one pair.  Default reproduces the reference's construction: euler_from_matrix(R, 'rxyz') then
+    euler_matrix(..., 'sxyz') (visual_odometry_v3.py:334, :140 -- equal to R only to first order, quirk B.4 kept);
+    ``exact_rotation`` puts R itself in the 4x4."""
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    t = np.asarray(t, dtype=np.float64).reshape(3) * scale
+    if exact_rotation:
+        M = np.eye(4)
+        M[:3, :3] = R
+        M[:3, 3] = t
+        return M
+    M4 = np.eye(4)
+    M4[:3, :3] = R
+    euler = transf.euler_from_matrix(M4, "rxyz")
+    return transf.translation_matrix(t).dot(transf.euler_matrix(euler[0], euler[1], euler[2], axes="sxyz"))
+
+
+def chain(relatives, start=None):
+    """Absolute poses T_0 = start, T_i = T_{i-1} . rel_i (visual_odometry_v3.py:367).  Returns n+1 matrices."""
+    cur = np.eye(4) if start is None else np.asarray(start, dtype=np.float64)
+    out = [cur]
+    for rel in relatives:
+        cur = cur.dot(rel)
+        out.append(cur)
+    return out
+
+
+def poses_to_relatives(poses, exact_rotation: bool = False):
+    """Per-pair 4x4s from dvo_pose records.  A pair whose status is not OK contributes the identity (the reference
+    would have raised inside cv.recoverPose; a batch runner must keep going -- SURVEY.md §5)."""
+    rel = []
+    for p in poses:
+        if int(p["status"]) != PAIR_OK:
+            rel.append(np.eye(4))
+        else:
+            rel.append(relative_transform(p["R"], p["t"], 1.0, exact_rotation))
+    return rel
+
+
+# ------------------------------------------------------------------------------------------------ writers (§8f rank 1)
+TRAJ_FILES = {"absolute": "stamped_traj_estimate_absolute.txt", "relative": "stamped_traj_estimate_relative.txt",
+              "velocity": "stamped_traj_estimate_velocity.txt", "legacy": "stamped_traj_estimate.txt"}
+
+
+def write_stamped(path, timestamps, transforms):
+    """Truncate, then one appended line per transform: ``ts tx ty tz qx qy qz qw \\n``
+    (trajectory_evaluation_dual_process.py:93-100 clear, :280-290 write; Shepperd quaternion [x,y,z,w])."""
+    PEM.clear_txt_file_contents(path)
+    with open(path, "a") as f:
+        for ts, T in zip(timestamps, transforms):
+            f.write(PEM.format_stamped_line(ts, PEM.translation_from_transformation_matrix(T), PEM.quaternion_from_transformation_matrix(T)))
+
+
+def write_trajectory(folder, timestamps, poses, start=None, exact_rotation: bool = False):
+    """Write the three stamped files of the current driver plus the legacy single file.
+
+    timestamps: n_frames values; poses: n_frames-1 dvo_pose records.  Rows (as the reference appends them,
+    trajectory_evaluation_dual_process.py:197-250): absolute has the seed pose then one row per pair; relative and
+    velocity have one row per pair stamped with the pair's second frame."""
+    os.makedirs(folder, exist_ok=True)
+    rel = poses_to_relatives(poses, exact_rotation)
+    absolute = chain(rel, start)
+    vel = [PEM.get_velocity_between_timestamps(r, timestamps[i], timestamps[i + 1]) for i, r in enumerate(rel)]
+    paths = {k: os.path.join(folder, v) for k, v in TRAJ_FILES.items()}
+    write_stamped(paths["absolute"], timestamps, absolute)
+    write_stamped(paths["relative"], timestamps[1:], rel)
+    write_stamped(paths["velocity"], timestamps[1:], vel)
+    write_stamped(paths["legacy"], timestamps, absolute)
+    return paths
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def gather_poses(local: np.ndarray, n_pairs: int, world_size: int, rank: int, group=None, device=None):
+    """All-gather the per-rank blocks of dvo_pose records into the full (n_pairs,) array on every rank.
+
+    One collective: every rank contributes ceil(n/G) records (short blocks are zero-padded), as raw bytes.  With an
+    NCCL group the buffers live on ``device`` (NVLink / NVSwitch); with gloo they stay on the host (CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    per = (n_pairs + world_size - 1) // world_size
+    rec = POSE_DTYPE.itemsize
+    buf = np.zeros(per, dtype=POSE_DTYPE)
+    buf[:len(local)] = local
+    send = torch.from_numpy(buf.view(np.uint8).copy())
+    if device is not None:
+        send = send.to(device)
+    recv = torch.empty(world_size * per * rec, dtype=torch.uint8, device=send.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    allp = recv.cpu().numpy().view(POSE_DTYPE)
+    out = np.zeros(n_pairs, dtype=POSE_DTYPE)
+    for r in range(world_size):
+        s, e = shard_pairs(n_pairs, world_size, r)
+        out[s:e] = allp[r * per:r * per + (e - s)]
+    return out
+
+
+def run_sharded(n_frames: int, compute_block, world_size: int = 1, rank: int = 0, group=None, device=None):
+    """``compute_block(first_frame, last_frame_inclusive) -> dvo_pose records`` for the rank's frames; returns the full
+    (n_frames-1,) record array on every rank.  world_size == 1 needs no process group."""
+    n_pairs = n_frames - 1
+    s, e = shard_pairs(n_pairs, world_size, rank)
+    local = compute_block(s, e) if e > s else np.zeros(0, dtype=POSE_DTYPE)
+    if len(local) != e - s:
+        raise ValueError("compute_block returned %d records for %d pairs" % (len(local), e - s))
+    if world_size == 1:
+        return local
+    return gather_poses(local, n_pairs, world_size, rank, group, device)
+
+
+class SequenceRunner:
+    """Consecutive-pair VO over device- or host-resident frames on one GPU (the unit each rank runs)."""
+
+    def __init__(self, width, height, K, nfeatures=500, batch=32, device=0, matcher=0, **kw):
+        from ._native import Context
+        self.K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+        self.ctx = Context(width, height, nfeatures=nfeatures, max_frames=batch + 1, matcher=matcher, device=device, **kw)
+
+    def run(self, frames):
+        """frames: (n, H, W) uint8 cuda tensor / host tensor / ndarray -> (n-1,) POSE_DTYPE."""
+        return self.ctx.sequence(frames, self.K)
+
+    def block_fn(self, frames):
+        """compute_block for run_sharded over a frame container indexable by slice (frames[a:b])."""
+        def fn(first, last):
+            return self.run(frames[first:last + 1])
+        return fn

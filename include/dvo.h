@@ -100,6 +100,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out);
 void dvo_destroy(dvo_ctx* ctx);
 const char* dvo_last_error(const dvo_ctx* ctx);
 const char* dvo_version(void);
+int dvo_sizeof(int which);                    /* 0 dvo_config, 1 dvo_pose, 2 dvo_features, 3 dvo_pair_arrays: binding self-check */
 int dvo_max_keypoints(const dvo_ctx* ctx);   /* capacity needed for dvo_features / dvo_pair_arrays */
 int dvo_max_frames(const dvo_ctx* ctx);
 long long dvo_kernel_launches(const dvo_ctx* ctx);   /* kernels launched by this context so far */
@@ -120,6 +121,16 @@ int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stre
  * sorted (:219-221), cv.KeyPoint_convert (:355,:358), cv.findEssentialMat (:297-300), cv.recoverPose (:303-306).
  * K is the 3x3 row-major camera matrix (host pointer, read before the call returns). */
 int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream);
+
+/* Overwrite one slot's keypoint coordinates and descriptors with caller data (kind 0 device, 1 host source;
+ * synchronises): lets get_matches_between_two_frames (:191-239) run on caller-supplied descriptors. */
+int dvo_set_features(dvo_ctx* ctx, int slot, const float* pt, const uint8_t* desc, int n, int kind, void* stream);
+
+/* findEssentialMat + recoverPose on caller correspondences (n x 2 float32 each; kind 0 device, 1 host source), result
+ * in pair slot `pair`: replaces get_transformation_between_two_frames' two cv2 calls (:297-306) and serves the
+ * RANSAC-heavy configuration (synthetic correspondences, no images). */
+int dvo_pose_points(dvo_ctx* ctx, int pair, const float* pts_prev, const float* pts_cur, int n, const double* K, int kind,
+                    void* stream);
 
 /* Copy n pair results (device->device or device->host, async on stream). kind: 0 device dst, 1 host dst. */
 int dvo_get_poses(dvo_ctx* ctx, int pair0, int n, dvo_pose* dst, int kind, void* stream);

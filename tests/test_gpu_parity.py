@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the oracle on identical inputs.
+
+Bars (BASELINE.json north star): integer stages bit-exact -- pyramid pixels, FAST scores / raster candidate lists,
+keypoint sets AND order, angles, Harris responses, descriptor bits, match indices and distances; pose within
+rotation <= 0.1 deg, translation direction <= 0.5 deg, inlier-mask IoU >= 0.95.
+The oracle is cv2 4.13.0 itself when importable on the box, else the numpy restatement pinned to it.
+"""
+import numpy as np
+import pytest
+
+from conftest import rot_err_deg, dir_err_deg, mask_iou
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL_DEG, TDIR_TOL_DEG, IOU_MIN = 0.1, 0.5, 0.95
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from droplet_visual_odometry_b200 import synth, _native
+    from oracle import orb_np, pose_np, chain_np, cv2_chain
+
+    class E:
+        pass
+    e = E()
+    e.torch, e.synth, e.native, e.O, e.P = torch, synth, _native, orb_np, pose_np
+    e.chain = cv2_chain if cv2_chain.available() else chain_np
+    e.frames, e.poses, e.K = synth.render_sequence(5, device="cuda")
+    e.fh = e.frames.cpu().numpy()
+    return e
+
+
+def check_pose(p, arr, ref):
+    assert p["status"] == 0
+    assert np.array_equal(arr["matches"], ref["matches"])
+    assert np.array_equal(arr["p_prev"], ref["p_prev"]) and np.array_equal(arr["p_cur"], ref["p_cur"])
+    E = p["E"].reshape(3, 3)
+    assert min(np.abs(E - ref["E"]).max(), np.abs(E + ref["E"]).max()) < 1e-4
+    assert mask_iou(arr["ransac_mask"], ref["ransac_mask"]) >= IOU_MIN
+    assert rot_err_deg(p["R"], ref["R"]) <= ROT_TOL_DEG
+    assert dir_err_deg(p["t"], ref["t"]) <= TDIR_TOL_DEG
+    assert mask_iou(arr["pose_mask"], ref["pose_mask"]) >= IOU_MIN
+    assert abs(int(p["n_good"]) - int(ref["good"])) <= max(2, 0.02 * len(ref["matches"]))
+
+
+# ----------------------------------------------------------------------------------------------- stages
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_stage_taps_bit_exact(env, use_tma):
+    ctx = env.native.Context(1280, 1024, nfeatures=2000, max_frames=2, use_tma=use_tma)
+    ctx.load_frames(env.frames[:1], 0)
+    ctx.orb(0, 1)
+    pyr = env.O.build_pyramid(env.fh[0])
+    for L in range(8):
+        assert ctx.level_size(L)[:2] == (pyr[L].shape[1], pyr[L].shape[0])
+        assert np.array_equal(ctx.tap_image(0, L, 0), pyr[L]), "pyramid level %d" % L
+        assert np.array_equal(ctx.tap_candidates(0, L), env.O.fast_detect(pyr[L], 20, 31)), "FAST candidates level %d" % L
+        assert np.array_equal(ctx.tap_image(0, L, 1), env.O.gaussian_blur_7x7(pyr[L])), "blur level %d" % L
+    ctx.close()
+
+
+@pytest.mark.parametrize("nf", [500, 2000])
+def test_features_bit_exact_and_order_exact(env, nf):
+    ctx = env.native.Context(1280, 1024, nfeatures=nf, max_frames=3)
+    ctx.load_frames(env.frames[:3], 0)
+    ctx.orb(0, 3)
+    for s in range(3):
+        f = ctx.features(s)
+        ref = env.chain.orb_features(env.fh[s], nf)
+        assert len(f["pt"]) == len(ref["pt"]) == nf
+        for k in ("pt", "size", "angle", "response", "octave", "desc"):
+            assert np.array_equal(f[k], ref[k]), (s, k)
+    ctx.close()
+
+
+def test_golden_fixture_through_cuda(env, golden):
+    nf = int(golden["nfeatures"])
+    ctx = env.native.Context(480, 360, nfeatures=nf, max_frames=2)
+    ctx.load_frames(np.stack([golden["frame0"], golden["frame1"]]), 0)
+    ctx.orb(0, 2)
+    for i in range(2):
+        f = ctx.features(i)
+        for k in ("pt", "size", "angle", "response", "octave", "desc"):
+            assert np.array_equal(f[k], golden["f%d_%s" % (i, k)]), (i, k)
+    ctx.pairs(0, 0, 1, golden["K"])
+    p = ctx.poses(0, 1)[0]
+    arr = ctx.pair_arrays(0, p["n_matches"])
+    assert np.array_equal(arr["matches"], golden["matches"])
+    assert mask_iou(arr["ransac_mask"], golden["ransac_mask"]) >= IOU_MIN
+    assert rot_err_deg(p["R"], golden["R"]) <= ROT_TOL_DEG and dir_err_deg(p["t"], golden["t"]) <= TDIR_TOL_DEG
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- whole pairs
+@pytest.mark.parametrize("nf", [500, 2000])
+def test_pairs_config1_config2(env, nf):
+    ctx = env.native.Context(1280, 1024, nfeatures=nf, max_frames=5)
+    ctx.load_frames(env.frames, 0)
+    ctx.orb(0, 5)
+    ctx.pairs(0, 0, 4, env.K)
+    ps = ctx.poses(0, 4)
+    feats = [env.chain.orb_features(env.fh[i], nf) for i in range(5)]
+    for i in range(4):
+        ref = env.chain.frame_pair(env.fh[i], env.fh[i + 1], env.K, nf, feats_prev=feats[i], feats_cur=feats[i + 1])
+        check_pose(ps[i], ctx.pair_arrays(i, ps[i]["n_matches"]), ref)
+    ctx.close()
+
+
+def test_sequence_runner_batches_and_host_frames(env):
+    """dvo_sequence with batch 2 (carry slot exercised), device and host sources, equals per-pair calls."""
+    big = env.native.Context(1280, 1024, nfeatures=500, max_frames=5)
+    big.load_frames(env.frames, 0); big.orb(0, 5); big.pairs(0, 0, 4, env.K)
+    ref = big.poses(0, 4)
+    small = env.native.Context(1280, 1024, nfeatures=500, max_frames=3)
+    dev = small.sequence(env.frames, env.K)
+    host = small.sequence(env.fh, env.K)
+    for a in (dev, host):
+        assert len(a) == 4
+        for i in range(4):
+            assert a[i]["status"] == 0 and np.array_equal(a[i]["R"], ref[i]["R"]) and np.array_equal(a[i]["t"], ref[i]["t"])
+            assert a[i]["n_matches"] == ref[i]["n_matches"] and a[i]["n_inliers"] == ref[i]["n_inliers"]
+    big.close(); small.close()
+
+
+def test_config4_high_density_knn_ratio(env):
+    nf = 10000
+    frames, _, K = env.synth.render_sequence(2, width=2448, height=2048, device="cuda")
+    fh = frames.cpu().numpy()
+    ctx = env.native.Context(2448, 2048, nfeatures=nf, max_frames=2, matcher=env.native.DVO_MATCH_KNN_RATIO)
+    ctx.load_frames(frames, 0); ctx.orb(0, 2); ctx.pairs(0, 0, 1, K)
+    p = ctx.poses(0, 1)[0]
+    ref = env.chain.frame_pair(fh[0], fh[1], K, nf, matcher="knn")
+    f0 = ctx.features(0)
+    for k in ("pt", "angle", "response", "octave", "desc"):
+        assert np.array_equal(f0[k], ref["feats_prev"][k]), k
+    check_pose(p, ctx.pair_arrays(0, p["n_matches"]), ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,outliers", [(1000, 0.4), (5000, 0.4), (20000, 0.4), (50000, 0.4)])
+def test_config5_ransac_heavy_points_only(env, n, outliers):
+    p1, p2, K, R, t, truth = env.synth.synthetic_correspondences(n, outliers, 0.3, seed=n)
+    ctx = env.native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=4096)
+    ctx.pose_points(p1, p2, K)
+    p = ctx.poses(0, 1)[0]
+    arr = ctx.pair_arrays(0, n)
+    ref = env.chain.pose_from_points(p1, p2, K, max_iters=4096)
+    assert p["status"] == 0 and p["n_matches"] == n
+    assert mask_iou(arr["ransac_mask"], ref["ransac_mask"]) >= IOU_MIN
+    assert rot_err_deg(p["R"], ref["R"]) <= ROT_TOL_DEG and dir_err_deg(p["t"], ref["t"]) <= TDIR_TOL_DEG
+    assert mask_iou(arr["pose_mask"], ref["pose_mask"]) >= IOU_MIN
+    # size-independent property: the recovered inliers are the true inliers
+    got = arr["ransac_mask"] > 0
+    assert (got & truth).sum() / max(1, truth.sum()) > 0.9 and (got & ~truth).sum() / max(1, got.sum()) < 0.05
+    assert rot_err_deg(p["R"], R) < 0.5
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- edge cases
+def test_textureless_and_low_texture_frames(env):
+    """No keypoints -> status TOO_FEW_MATCHES (cv.findEssentialMat would return None); few candidates -> retainBest's
+    'count <= n' early-outs keep raster order."""
+    flat = np.full((2, 480, 640), 90, np.uint8)
+    ctx = env.native.Context(640, 480, nfeatures=500, max_frames=2)
+    ctx.load_frames(flat, 0); ctx.orb(0, 2); ctx.pairs(0, 0, 1, env.synth.camera_matrix(640, 480))
+    p = ctx.poses(0, 1)[0]
+    assert len(ctx.features(0)["pt"]) == 0 and p["status"] == env.native.PAIR_TOO_FEW_MATCHES and p["n_matches"] == 0
+    sparse = flat.copy()
+    rng = np.random.default_rng(3)
+    for _ in range(40):      # a handful of bright squares: far fewer corners than any level's quota
+        x, y = int(rng.integers(60, 560)), int(rng.integers(60, 400))
+        sparse[:, y:y + 12, x:x + 12] = 220
+    sparse[1] = np.roll(sparse[1], 3, axis=1)
+    ctx.load_frames(sparse, 0); ctx.orb(0, 2)
+    for s in range(2):
+        f = ctx.features(s)
+        ref = env.chain.orb_features(sparse[s], 500)
+        assert 0 < len(ref["pt"]) < 500 and len(f["pt"]) == len(ref["pt"])
+        for k in ("pt", "angle", "response", "octave", "desc"):
+            assert np.array_equal(f[k], ref[k]), k
+    ctx.close()
+
+
+def test_ragged_sizes_not_multiples_of_the_tile(env):
+    for (w, h) in ((333, 257), (641, 479)):
+        frames, _, K = env.synth.render_sequence(2, width=w, height=h, device="cuda")
+        fh = frames.cpu().numpy()
+        ctx = env.native.Context(w, h, nfeatures=300, max_frames=2)
+        ctx.load_frames(frames, 0); ctx.orb(0, 2)
+        for s in range(2):
+            f = ctx.features(s)
+            ref = env.chain.orb_features(fh[s], 300)
+            assert len(f["pt"]) == len(ref["pt"])
+            for k in ("pt", "angle", "response", "octave", "desc"):
+                assert np.array_equal(f[k], ref[k]), (w, h, k)
+        ctx.close()
+
+
+def test_errors_are_reported_not_swallowed(env):
+    ctx = env.native.Context(640, 480, nfeatures=100, max_frames=2)
+    with pytest.raises(env.native.DvoError):
+        ctx.orb(1, 5)                      # slot range out of bounds
+    with pytest.raises(env.native.DvoError):
+        ctx.pairs(1, 0, 1, np.eye(3))      # needs slot 2
+    with pytest.raises(env.native.DvoError):
+        env.native.Context(8192, 480)      # > 4096
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- drop-in class
+def test_visual_odometry_dropin_matches_reference_chain(env):
+    from droplet_visual_odometry_b200.visual_odometry_v3 import VisualOdometry
+    from droplet_visual_odometry_b200 import sequence as S
+    vo = VisualOdometry(camera_matrix=env.K, nfeatures=500)
+    pose0 = vo.robot_curr_position
+    cur, rel = vo.visual_odometry_calculations(env.fh[1], env.fh[2], pose0, None, None)
+    ref = env.chain.frame_pair(env.fh[1], env.fh[2], env.K, 500)
+    assert rot_err_deg(vo.last_pair["R"], ref["R"]) <= ROT_TOL_DEG and dir_err_deg(vo.last_pair["t"], ref["t"]) <= TDIR_TOL_DEG
+    assert np.allclose(rel, S.relative_transform(vo.last_pair["R"], vo.last_pair["t"])) and np.allclose(cur, pose0.dot(rel))
+    assert np.allclose(vo.essential_matrix, vo.last_pair["E"]) and len(vo.frame_translations) == 1
+    # the step-by-step public methods give the same answer as the fused call
+    kp1, d1, _ = vo.compute_current_image_elements(env.fh[1])
+    kp2, d2, _ = vo.compute_current_image_elements(env.fh[2])
+    assert np.array_equal(d1, ref["feats_prev"]["desc"]) and len(kp1) == 500 and kp1[0].pt == tuple(ref["feats_prev"]["pt"][0])
+    matches, top_prev, top_cur = vo.get_matches_between_two_frames(kp1, d1, kp2, d2)
+    assert [(m.queryIdx, m.trainIdx, int(m.distance)) for m in matches] == [tuple(r) for r in ref["matches"].tolist()]
+    cur2, rel2 = vo.previous_current_matching(top_prev, top_cur, pose0, None, None)
+    assert np.allclose(rel2, rel) and np.allclose(cur2, cur)
+    R, t, pa, pb, raw = vo.relative_pose(env.fh[1], env.fh[2])
+    assert np.array_equal(pa, ref["p_prev"]) and R.shape == (3, 3) and t.shape == (3, 1)
