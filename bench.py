@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark: frame-pairs/sec of the per-frame-pair VO hot path (ORB detect/describe -> BF Hamming match ->
+E-RANSAC -> recoverPose) on synthetic textured 1280x1024 mono frames, ORB 2000 features (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            (under torchrun for N > 1: one rank per GPU)
+  python bench.py --impl reference ...                     the reference's cv2 CPU path on the box's host cores
+
+A step = one batch of --batch consecutive new frames of the sequence (= --batch frame pairs; the last frame of the
+previous batch is carried, its features are not recomputed).  Timed region: K steps bracketed by barrier + sync, CUDA
+events on the launching stream, max over ranks; frames are resident in HBM (value) or in pinned host memory (e2e).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frame-pairs/sec (ORB+match+E-RANSAC+pose)"
+UNIT = "frame-pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=50, help="new frames (= pairs) per step")
+    ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--nfeatures", type=int, default=2000)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=0, help="reference arm: pairs per step (0 = 2 x workers, min 8)")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "synthetic sequence %dx%d mono, ORB %d feats, 8 levels, crossCheck BF-Hamming, findEssentialMat RANSAC(0.999, 1px, 1000 it), recoverPose; consecutive-pair VO" % (
+        a.width, a.height, a.nfeatures)
+
+
+# ================================================================================================ CPU reference (cv2)
+def _ref_worker_init(path, kpath, nf):
+    global _F, _K, _NF
+    import cv2
+    cv2.setNumThreads(1)
+    _F = np.load(path, mmap_mode="r")
+    _K = np.load(kpath)
+    _NF = nf
+
+
+def _ref_worker_pair(i):
+    from oracle import cv2_chain
+    r = cv2_chain.frame_pair(np.ascontiguousarray(_F[i]), np.ascontiguousarray(_F[i + 1]), _K, _NF)   # both frames' ORB per pair,
+    return int(len(r["matches"]))                                                                    # as visual_odometry_v3.py:387-392
+
+
+class CpuReference:
+    """The reference's per-pair chain through cv2 (oracle/cv2_chain.py), one worker process per host core over
+    independent pairs, cv2 internal threading off in each worker.  Falls back to the numpy port only if cv2 is absent."""
+
+    def __init__(self, frames_u8: np.ndarray, K: np.ndarray, nfeatures: int, workers: int | None = None):
+        import multiprocessing as mp
+        from oracle import cv2_chain
+        self.kind = "reference" if cv2_chain.available() else "port"
+        self.n_pairs = len(frames_u8) - 1
+        self.workers = workers or (os.cpu_count() or 1)
+        if self.kind == "port":
+            self.workers = 1
+            self.frames, self.K, self.nf = frames_u8, K, nfeatures
+            return
+        self.tmp = tempfile.mkdtemp(prefix="dvo_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self.path, self.kpath = os.path.join(self.tmp, "frames.npy"), os.path.join(self.tmp, "K.npy")
+        np.save(self.path, frames_u8)
+        np.save(self.kpath, np.asarray(K, dtype=np.float64))
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_ref_worker_init, initargs=(self.path, self.kpath, nfeatures))
+        self.pool.map(_ref_worker_pair, [0] * self.workers)     # spin every worker up (imports, cv2 init)
+
+    def run_pairs(self, idx):
+        if self.kind == "port":
+            from oracle import chain_np
+            for i in idx:
+                chain_np.frame_pair(self.frames[i], self.frames[i + 1], self.K, self.nf)
+            return
+        self.pool.map(_ref_worker_pair, list(idx), chunksize=1)
+
+    def close(self):
+        if self.kind == "reference":
+            self.pool.close()
+            self.pool.join()
+            for f in (self.path, self.kpath):
+                os.remove(f)
+            os.rmdir(self.tmp)
+
+
+def render_host_frames(n, a, start_index=0):
+    import torch
+    from droplet_visual_odometry_b200 import synth
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    frames, _, K = synth.render_sequence(n, a.width, a.height, device=dev, start_index=start_index)
+    return frames.cpu().numpy(), K
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    pps = a.ref_pairs_per_step or max(8, 2 * workers)
+    pps = min(pps, 256)
+    frames, K = render_host_frames(pps + 1, a)
+    ref = CpuReference(frames, K, a.nfeatures, workers)
+    for _ in range(max(a.warmup, 0)):
+        ref.run_pairs(range(min(pps, workers)))
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ref.run_pairs(range(pps))
+    dt = time.perf_counter() - t0
+    ref.close()
+    value = a.steps * pps / dt
+    sample = "%d steps x %d independent frame pairs (both frames' ORB recomputed per pair), %d worker processes, cv2 threads=1 each" % (
+        a.steps, pps, ref.workers)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+           "data": "synthetic", "config": {"workload": workload_name(a), "pairs_per_step": pps, "cpu": cpu_model()},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.workers, "kind": ref.kind, "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ================================================================================================ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ================================================================================================ B200 arm
+def level_pixel_counts(ctx):
+    return [ctx.level_size(L)[0] * ctx.level_size(L)[1] for L in range(ctx.nlevels)]
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from droplet_visual_odometry_b200 import synth, _native
+    from droplet_visual_odometry_b200._native import POSE_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K_steps, W_steps = a.batch, a.steps, a.warmup
+    n_frames = (K_steps + W_steps) * B + 1
+    frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * 5000)
+    ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local)
+    rec = POSE_DTYPE.itemsize
+    poses_dev = torch.zeros((K_steps + W_steps) * B * rec, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * K_steps * B * rec, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_pass(first_step, nsteps, fresh):
+        """nsteps batches from HBM-resident frames; returns #pairs"""
+        pairs = 0
+        for s in range(first_step, first_step + nsteps):
+            lo = s * B + (0 if (fresh and s == first_step) else 1)
+            hi = (s + 1) * B + 1
+            out = poses_dev[pairs * rec + first_step * B * rec:]
+            pairs += ctx.sequence_step(frames[lo:hi], Kmat, out, first=(fresh and s == first_step))
+        return pairs
+
+    # ---- warm-up (also primes the carry slot so every timed step is B pairs)
+    device_pass(0, W_steps, fresh=True)
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    npairs = device_pass(W_steps, K_steps, fresh=False)
+    if world > 1:   # the path's one exchange step: all-gather of the per-pair (R, t, status) records
+        dist.all_gather_into_tensor(gathered, poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.kernel_launches - launches0
+    assert npairs == K_steps * B
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * npairs / (ms / 1e3)
+    host_poses = poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec].cpu().numpy().view(POSE_DTYPE)
+    ok_frac = float(np.mean(host_poses["status"] == 0))
+
+    # ---- end to end through the public API: pinned host frames in, pose records out, every step
+    e2e_frames = frames[W_steps * B:(W_steps + K_steps) * B + 1].cpu().pin_memory()
+    poses_host_t = torch.empty(K_steps * B * rec, dtype=torch.uint8).pin_memory()
+    poses_host = poses_host_t.numpy().view(POSE_DTYPE)
+
+    def host_pass(nsteps, fresh_first=True):
+        pairs = 0
+        for s in range(nsteps):
+            lo = s * B + (0 if s == 0 else 1)
+            pairs += ctx.sequence_step(e2e_frames[lo:(s + 1) * B + 1], Kmat, poses_host[pairs:], first=(s == 0))
+        ctx.sync()
+        return pairs
+    host_pass(min(2, K_steps))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pairs = host_pass(K_steps)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_pairs / e2e_s
+
+    # ---- roofline pass: the same K steps again with per-kernel CUDA events on the launching stream
+    roofline, stages = None, None
+    if rank == 0:
+        ctx.profile(True)
+        ctx.profile_collect()
+        device_pass(W_steps, K_steps, fresh=False)
+        prof = ctx.profile_collect()
+        ctx.profile(False)
+        px = level_pixel_counts(ctx)
+        total_px = sum(px)
+        pyr_bytes = sum(px[L - 1] + px[L] for L in range(1, len(px)))
+        alg_bytes_per_frame = {"k_pyr_down": pyr_bytes, "k_fast_nms": total_px, "k_blur": 2 * total_px}
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        stages = {}
+        nkp = a.nfeatures
+        for name, (tms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            if cnt == 0:
+                continue
+            st = {"ms_total": round(tms, 3), "share": round(tms / tot_ms, 4), "launch_groups": cnt}
+            if name in alg_bytes_per_frame:
+                # one launch group covers B frames (k_pyr_down: 7 launches per batch, summed)
+                groups = cnt / (7 if name == "k_pyr_down" else 1)
+                bytes_total = alg_bytes_per_frame[name] * B * groups
+                st["achieved_GBps"] = round(bytes_total / (tms * 1e-3) / 1e9, 2)
+                st["frac_of_hbm_peak"] = round(st["achieved_GBps"] / peak, 4)
+            if name == "k_nn":
+                st["gpopc_per_s"] = round(2 * nkp * nkp * 8 * B * cnt / (tms * 1e-3) / 1e9, 1)
+            stages[name] = st
+        dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+        dms, dcnt = prof[dom]
+        if dom in alg_bytes_per_frame:
+            groups = dcnt / (7 if dom == "k_pyr_down" else 1)
+            alg = alg_bytes_per_frame[dom] * B
+            achieved = alg * groups / (dms * 1e-3) / 1e9
+        else:
+            # not a streaming kernel: its algorithmic HBM bytes are the records it must read and write per batch
+            per_pair = {"k_nn": 2 * nkp * 32 * 2 + nkp * 16, "k_select": total_px // 256 * 4, "k_solve": 128 * 10 * 72,
+                        "k_score": nkp * 32 + 128 * 10 * 76, "k_cheirality": nkp * 33}.get(dom, nkp * 32)
+            alg = per_pair * B
+            achieved = alg * dcnt / (dms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+                    "share_of_step": round(dms / tot_ms, 4), "algorithmic_bytes_per_launch": int(alg),
+                    "avg_launch_ms": round(dms / max(dcnt, 1), 4)}
+
+    # ---- CPU baseline beside it (rank 0, bounded sample of the same workload)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        pps = min(max(8, 2 * workers), 128)
+        fr = frames[:pps + 1].cpu().numpy()
+        ref = CpuReference(fr, Kmat, a.nfeatures, workers)
+        t0 = time.perf_counter()
+        done = 0
+        while True:
+            ref.run_pairs(range(pps))
+            done += pps
+            if time.perf_counter() - t0 >= a.cpu_baseline_seconds:
+                break
+        dt = time.perf_counter() - t0
+        ref.close()
+        cpu = {"value": done / dt, "unit": UNIT, "cores": ref.workers, "kind": ref.kind, "cpu": cpu_model(),
+               "sample": "%d frame pairs of the same sequence in %.1f s: cv2 chain, both frames' ORB recomputed per pair as the reference does, one worker process per core (cv2 threads=1 each)" % (done, dt)}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
+               "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
+               "data": "synthetic",
+               "config": {"workload": workload_name(a), "pairs_per_step": B, "frames_resident_MB": round(frames.numel() / 1e6, 1),
+                          "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
+                              B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
+                          "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
+                          "pairs_ok_fraction": ok_frac},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height, "d2h_bytes_per_step": B * rec},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

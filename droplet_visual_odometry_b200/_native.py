@@ -79,6 +79,13 @@ def load_library():
     lib.dvo_get_poses.argtypes = [vp, ci, ci, vp, ci, vp]
     lib.dvo_get_pair_arrays.argtypes = [vp, ci, ctypes.POINTER(dvo_pair_arrays), vp]
     lib.dvo_sequence.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, vp]
+    lib.dvo_sequence_step.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, ci, vp]
+    lib.dvo_profile_enable.argtypes = [ci]
+    lib.dvo_profile_enable.restype = None
+    lib.dvo_profile_collect.argtypes = [vp, vp, ci]
+    lib.dvo_profile_name.argtypes = [ci]
+    lib.dvo_profile_name.restype = ctypes.c_char_p
+    lib.dvo_sizeof.argtypes = [ci]
     lib.dvo_level_size.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.dvo_tap_image.argtypes = [vp, ci, ci, ci, vp, vp]
     lib.dvo_tap_candidates.argtypes = [vp, ci, ci, vp, ci, ctypes.POINTER(ci), vp]
@@ -260,6 +267,31 @@ class Context:
         self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
                                           poses.ctypes.data, 1, self._stream()), "dvo_sequence")
         return poses
+
+    def sequence_step(self, frames, K, poses_out, first):
+        """One batch: frames (n, H, W) uint8 -- cuda tensor with poses_out a cuda uint8 tensor (async), or pinned/pageable
+        host tensor with poses_out a POSE_DTYPE ndarray.  Returns the number of records written."""
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        n = frames.shape[0]
+        if frames.is_cuda:
+            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+                                            poses_out.data_ptr(), 0, int(bool(first)), self._stream())
+        else:
+            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+                                            poses_out.ctypes.data, 1, int(bool(first)), self._stream())
+        if rc < 0:
+            self._check(rc, "dvo_sequence_step")
+        return rc
+
+    def profile(self, on):
+        self.lib.dvo_profile_enable(int(bool(on)))
+
+    def profile_collect(self):
+        """{kernel name: (total ms, launch groups)} since the previous collect; synchronises."""
+        ms = np.zeros(32, dtype=np.float64)
+        cnt = np.zeros(32, dtype=np.int32)
+        n = self.lib.dvo_profile_collect(ms.ctypes.data, cnt.ctypes.data, 32)
+        return {self.lib.dvo_profile_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     # ------------------------------------------------------------------ taps
     def tap_image(self, slot, level, which=0):

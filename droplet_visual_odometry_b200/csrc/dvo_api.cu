@@ -11,6 +11,8 @@ long long orb_launch_count();
 long long pair_launch_count();
 void orb_kernels_init();
 void pair_kernels_init(int sortBytes);
+void prof_enable(bool on);
+void prof_collect(double* ms, int* count, int n);
 }  // namespace dvo
 
 using namespace dvo;
@@ -32,6 +34,7 @@ struct dvo_ctx {
     dvo_pose* h_poseStage = nullptr;   // pinned staging for the host sequence runner
     uint8_t* h_frameStage = nullptr;
     long long launchBase = 0;
+    int carrySlot = -1;                // slot holding the last frame of the previous dvo_sequence_step
 };
 
 #define CK(call)                                                                                     \
@@ -491,39 +494,68 @@ __global__ void k_copy_features(OrbGeom g, OrbBuffers b, int src, int dst) {
     }
 }
 
+int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pitch, size_t frame_stride, const double* K,
+                      dvo_pose* poses, int kind, int first, void* stream) {
+    if (!ctx || !frames || !K || !poses || n_new < 1) {
+        if (ctx) ctx->err = "dvo_sequence_step: bad arguments";
+        return DVO_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (first || ctx->carrySlot < 0) {
+        if (n_new > ctx->nSlots) { ctx->err = "dvo_sequence_step: more frames than slots"; return DVO_E_CAPACITY; }
+        if ((rc = dvo_load_frames(ctx, frames, n_new, pitch, frame_stride, 0, kind, st)) != 0) return rc;
+        if ((rc = dvo_orb(ctx, 0, n_new, st)) != 0) return rc;
+        if (n_new > 1) {
+            if ((rc = dvo_pairs(ctx, 0, 0, n_new - 1, K, st)) != 0) return rc;
+            if ((rc = dvo_get_poses(ctx, 0, n_new - 1, poses, kind, st)) != 0) return rc;
+        }
+        ctx->carrySlot = n_new - 1;
+        return n_new - 1;
+    }
+    if (n_new > ctx->nSlots - 1) { ctx->err = "dvo_sequence_step: more new frames than slots - 1"; return DVO_E_CAPACITY; }
+    if (ctx->carrySlot != 0) {
+        k_copy_features<<<32, 256, 0, st>>>(ctx->og, ctx->ob, ctx->carrySlot, 0);
+        CK(cudaGetLastError());
+    }
+    if ((rc = dvo_load_frames(ctx, frames, n_new, pitch, frame_stride, 1, kind, st)) != 0) return rc;
+    if ((rc = dvo_orb(ctx, 1, n_new, st)) != 0) return rc;
+    if ((rc = dvo_pairs(ctx, 0, 0, n_new, K, st)) != 0) return rc;
+    if ((rc = dvo_get_poses(ctx, 0, n_new, poses, kind, st)) != 0) return rc;
+    ctx->carrySlot = n_new;
+    return n_new;
+}
+
 int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride, const double* K,
                  dvo_pose* poses, int kind, void* stream) {
     if (!ctx || !frames || !K || !poses || n_frames < 2) {
         if (ctx) ctx->err = "dvo_sequence: bad arguments";
         return DVO_E_INVALID;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const int B = ctx->nSlots - 1;   // new frames per batch after the first
-    int done = 0;                    // frames whose features exist
-    int rc;
-    // first batch: up to nSlots frames into slots 0..
-    int n0 = std::min(n_frames, ctx->nSlots);
-    if ((rc = dvo_load_frames(ctx, frames, n0, pitch, frame_stride, 0, kind, st)) != 0) return rc;
-    if ((rc = dvo_orb(ctx, 0, n0, st)) != 0) return rc;
-    if ((rc = dvo_pairs(ctx, 0, 0, n0 - 1, K, st)) != 0) return rc;
-    if ((rc = dvo_get_poses(ctx, 0, n0 - 1, poses, kind, st)) != 0) return rc;
-    done = n0;
-    int carry = n0 - 1;              // slot holding the last processed frame's features
+    int done = std::min(n_frames, ctx->nSlots);
+    int rc = dvo_sequence_step(ctx, frames, done, pitch, frame_stride, K, poses, kind, 1, stream);
+    if (rc < 0) return rc;
     while (done < n_frames) {
         int nb = std::min(B, n_frames - done);
-        if (carry != 0) {
-            k_copy_features<<<32, 256, 0, st>>>(ctx->og, ctx->ob, carry, 0);
-            CK(cudaGetLastError());
-        }
-        if ((rc = dvo_load_frames(ctx, frames + (size_t)done * frame_stride, nb, pitch, frame_stride, 1, kind, st)) != 0) return rc;
-        if ((rc = dvo_orb(ctx, 1, nb, st)) != 0) return rc;
-        if ((rc = dvo_pairs(ctx, 0, 0, nb, K, st)) != 0) return rc;
-        if ((rc = dvo_get_poses(ctx, 0, nb, poses + (done - 1), kind, st)) != 0) return rc;
-        carry = nb;
+        rc = dvo_sequence_step(ctx, frames + (size_t)done * frame_stride, nb, pitch, frame_stride, K, poses + (done - 1), kind, 0, stream);
+        if (rc < 0) return rc;
         done += nb;
     }
-    if (kind == 1) CK(cudaStreamSynchronize(st));
+    if (kind == 1) CK(cudaStreamSynchronize((cudaStream_t)stream));
     return DVO_OK;
+}
+
+void dvo_profile_enable(int on) { prof_enable(on != 0); }
+int dvo_profile_collect(double* ms, int* count, int n) {
+    if (!ms || !count || n < 1) return DVO_E_INVALID;
+    prof_collect(ms, count, n);
+    return PF_COUNT;
+}
+const char* dvo_profile_name(int id) {
+    static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_compact", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
+                                          "k_match_sort", "k_solve", "k_score", "k_replay", "k_pose_prep", "k_cheirality", "k_pose_final"};
+    return (id >= 0 && id < PF_COUNT) ? names[id] : "";
 }
 
 }  // extern "C"

@@ -114,6 +114,17 @@ struct PairBuffers {
     PoseScratch* poseScratch;   // [pairs]
 };
 
+// ---- per-kernel CUDA-event profiler (bench.py's roofline pass; off by default, zero cost when off)
+enum ProfId { PF_PYR = 0, PF_FAST, PF_COMPACT, PF_SELECT, PF_ANGLE, PF_BLUR, PF_BRIEF, PF_NN, PF_SORT, PF_SOLVE, PF_SCORE, PF_REPLAY,
+              PF_POSE_PREP, PF_CHEIRALITY, PF_POSE_FINAL, PF_COUNT };
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+struct ProfScope {
+    int id; cudaStream_t st;
+    ProfScope(int i, cudaStream_t s) : id(i), st(s) { prof_begin(id, st); }
+    ~ProfScope() { prof_end(id, st); }
+};
+
 // ---- launchers (orb_kernels.cu / pair_kernels.cu) ---------------------------------------------------------------
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st);

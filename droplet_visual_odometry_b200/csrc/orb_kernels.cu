@@ -569,6 +569,38 @@ __global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot
 static long long g_launches = 0;
 long long orb_launch_count() { return g_launches; }
 
+struct ProfRec { int id; cudaEvent_t a, b; };
+static bool g_profOn = false;
+static std::vector<ProfRec> g_profRecs;
+static std::vector<cudaEvent_t> g_profPool;
+static cudaEvent_t prof_event() {
+    if (!g_profPool.empty()) { cudaEvent_t e = g_profPool.back(); g_profPool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int id, cudaStream_t st) {
+    if (!g_profOn) return;
+    ProfRec r{id, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_profRecs.push_back(r);
+}
+void prof_end(int id, cudaStream_t st) {
+    if (!g_profOn) return;
+    for (size_t i = g_profRecs.size(); i-- > 0;)
+        if (g_profRecs[i].id == id) { cudaEventRecord(g_profRecs[i].b, st); return; }
+}
+void prof_enable(bool on) { g_profOn = on; }
+// total milliseconds and launch-group counts per id since the last collect (synchronises the device)
+void prof_collect(double* ms, int* count, int n) {
+    cudaDeviceSynchronize();
+    for (int i = 0; i < n; ++i) { ms[i] = 0; count[i] = 0; }
+    for (auto& r : g_profRecs) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.id < n) { ms[r.id] += t; count[r.id] += 1; }
+        g_profPool.push_back(r.a); g_profPool.push_back(r.b);
+    }
+    g_profRecs.clear();
+}
+
 // DVO_DEBUG_SYNC=1: synchronise and report after every kernel (debug only)
 bool debug_sync_enabled() {
     static int v = -1;
@@ -588,30 +620,32 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
     for (int L = 1; L < g.nlevels; ++L) {
         dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 7) / 8, nSlots);
+        ProfScope ps_(PF_PYR, st);
         k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0);
         ++g_launches;
         debug_sync("k_pyr_down", st);
     }
     {
         dim3 grid(g.tilesPerFrame, nSlots);
+        ProfScope ps_(PF_FAST, st);
         if (useTma) k_fast_nms<true><<<grid, 256, 0, st>>>(g, b, *tmaps, slot0);
         else k_fast_nms<false><<<grid, 256, 0, st>>>(g, b, *tmaps, slot0);
         ++g_launches;
         debug_sync("k_fast_nms", st);
     }
-    k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0);
+    { ProfScope ps_(PF_COMPACT, st); k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_compact", st);
-    k_select<<<dim3(g.nlevels, nSlots), 256, kSelectSmemBytes, st>>>(g, b, slot0);
+    { ProfScope ps_(PF_SELECT, st); k_select<<<dim3(g.nlevels, nSlots), 256, kSelectSmemBytes, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_select", st);
-    k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0);
+    { ProfScope ps_(PF_ANGLE, st); k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_angle_pack", st);
-    k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, st>>>(g, b, slot0);
+    { ProfScope ps_(PF_BLUR, st); k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_blur", st);
-    k_brief<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0);
+    { ProfScope ps_(PF_BRIEF, st); k_brief<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_brief", st);
 }

@@ -394,19 +394,19 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
     const float t32 = (float)(thr * thr);
     PoseScratch* ps = pb.poseScratch;
     for (int c = 0; c < pg.nChunks; ++c) {
-        k_solve<<<nPairs, kRansacChunk, 0, st>>>(pg, pb, pair0, c);
+        { ProfScope ps_(PF_SOLVE, st); k_solve<<<nPairs, kRansacChunk, 0, st>>>(pg, pb, pair0, c); }
         debug_sync("k_solve", st);
-        k_score<<<dim3(kRansacChunk * kMaxModels / 8, nPairs), 256, 0, st>>>(pg, pb, pair0, c, t32);
+        { ProfScope ps_(PF_SCORE, st); k_score<<<dim3(kRansacChunk * kMaxModels / 8, nPairs), 256, 0, st>>>(pg, pb, pair0, c, t32); }
         debug_sync("k_score", st);
-        k_replay<<<(nPairs + 63) / 64, 64, 0, st>>>(pg, pb, pair0, nPairs, c);
+        { ProfScope ps_(PF_REPLAY, st); k_replay<<<(nPairs + 63) / 64, 64, 0, st>>>(pg, pb, pair0, nPairs, c); }
         g_pair_launches += 3;
         debug_sync("k_replay", st);
     }
-    k_pose_prep<<<nPairs, 256, 0, st>>>(pg, pb, ps, pair0, t32);
+    { ProfScope ps_(PF_POSE_PREP, st); k_pose_prep<<<nPairs, 256, 0, st>>>(pg, pb, ps, pair0, t32); }
     debug_sync("k_pose_prep", st);
-    k_cheirality<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(pg, pb, ps, pair0);
+    { ProfScope ps_(PF_CHEIRALITY, st); k_cheirality<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(pg, pb, ps, pair0); }
     debug_sync("k_cheirality", st);
-    k_pose_final<<<nPairs, 256, 0, st>>>(og, ob, pg, pb, ps, slotA0, pair0);
+    { ProfScope ps_(PF_POSE_FINAL, st); k_pose_final<<<nPairs, 256, 0, st>>>(og, ob, pg, pb, ps, slotA0, pair0); }
     g_pair_launches += 3;
     debug_sync("k_pose_final", st);
 }
@@ -415,8 +415,8 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
                   int nPairs, const double* K, cudaStream_t st) {
     if (nPairs <= 0) return;
     const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-    k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
-    k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy);
+    { ProfScope ps_(PF_NN, st); k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0); }
+    { ProfScope ps_(PF_SORT, st); k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy); }
     g_pair_launches += 2;
     debug_sync("k_nn+sort", st);
     launch_ransac_pose(og, ob, pg, pb, slotA0, pair0, nPairs, K, st);

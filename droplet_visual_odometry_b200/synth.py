@@ -75,16 +75,20 @@ class CameraPose:
     C: np.ndarray
 
 
-def trajectory(n_frames: int, period: int = 48) -> list:
-    """Closed smooth path: a 1.5 m circle in the x-z plane with small yaw/pitch/roll oscillation.
+def trajectory(n_frames: int, period: int = 48, start_index: int = 0) -> list:
+    """Smooth path: a 1.5 m circle in the x-z plane (one lap per ``period`` frames) with small yaw/pitch/roll
+    oscillation, plus slow incommensurate drifts so that no two frames of a long sequence are identical.
 
-    Per step: translation ~0.094 m (1-3 % of the 3.4-10 m scene depth), rotation < 0.3 deg.
+    Per step: translation ~0.2 m (2-6 % of the 3.4-10 m scene depth, i.e. depth/baseline < 50 = cv2's recoverPose
+    distance threshold for most points), rotation < 0.5 deg.
     """
     poses = []
-    for i in range(n_frames):
+    for i in range(start_index, start_index + n_frames):
         th = 2.0 * math.pi * i / period
-        C = np.array([1.5 * math.sin(th), 0.15 * math.sin(2.0 * th), 1.5 * (1.0 - math.cos(th))], dtype=np.float64)
-        yaw = math.radians(3.0) * math.sin(th + 0.7)
+        C = np.array([1.5 * math.sin(th) + 0.25 * math.sin(2.0 * math.pi * i / 1013.0),
+                      0.15 * math.sin(2.0 * th) + 0.1 * math.sin(2.0 * math.pi * i / 733.0),
+                      1.5 * (1.0 - math.cos(th))], dtype=np.float64)
+        yaw = math.radians(3.0) * math.sin(th + 0.7) + math.radians(1.0) * math.sin(2.0 * math.pi * i / 911.0)
         pitch = math.radians(1.5) * math.sin(2.0 * th + 0.2)
         roll = math.radians(2.0) * math.cos(th)
         poses.append(CameraPose(R=_rot_xyz(pitch, yaw, roll), C=C))
@@ -151,10 +155,10 @@ def render_frame(pose: CameraPose, width: int, height: int, texture: torch.Tenso
 
 
 def render_sequence(n_frames: int, width: int = 1280, height: int = 1024, device="cpu", period: int = 48,
-                    seed: int = TEXTURE_SEED, texture_size: int = TEXTURE_SIZE):
+                    seed: int = TEXTURE_SEED, texture_size: int = TEXTURE_SIZE, start_index: int = 0):
     """Returns (frames u8 (n, H, W) tensor on ``device``, poses, K)."""
     tex = torch.from_numpy(make_texture(seed, texture_size)).to(device=device, dtype=torch.float32)
-    poses = trajectory(n_frames, period)
+    poses = trajectory(n_frames, period, start_index)
     frames = torch.empty((n_frames, height, width), dtype=torch.uint8, device=device)
     for i, p in enumerate(poses):
         frames[i] = render_frame(p, width, height, tex)

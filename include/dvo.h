@@ -142,6 +142,18 @@ int dvo_get_pair_arrays(dvo_ctx* ctx, int pair, const dvo_pair_arrays* out, void
 int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch, size_t frame_stride, const double* K,
                  dvo_pose* poses, int kind, void* stream);
 
+/* One batch of a longer sequence: `first` != 0 starts a sequence (n_new frames -> n_new-1 pairs); otherwise the last
+ * frame of the previous call is carried (its features are kept, not recomputed) and n_new frames give n_new pairs.
+ * Returns the number of pose records written (>= 0) or a negative error.  Asynchronous for device memory. */
+int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pitch, size_t frame_stride, const double* K,
+                      dvo_pose* poses, int kind, int first, void* stream);
+
+/* Per-kernel CUDA-event timing for the roofline report (process-wide switch; collect synchronises the device and
+ * returns the number of kernel ids; ms/count are totals since the previous collect). */
+void dvo_profile_enable(int on);
+int dvo_profile_collect(double* ms, int* count, int n);
+const char* dvo_profile_name(int id);
+
 /* Stage taps for the parity tests (device destination, tightly packed rows of `w` bytes unless noted). */
 int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota);
 int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which /*0 pyramid, 1 blurred, 2 nms score map*/,
