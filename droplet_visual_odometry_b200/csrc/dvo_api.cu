@@ -223,6 +223,8 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     DA(b.cand, S * g.candPerSlot);
     DA(b.candCount, S * kMaxLevels);
     DA(b.pairs, S * g.candPerSlot);
+    DA(b.selWork, S * g.candPerSlot);
+    DA(b.selList, S * g.candPerSlot * 2);
     DA(b.finXY, S * g.finPerSlot);
     DA(b.finResp, S * g.finPerSlot);
     DA(b.finCount, S * kMaxLevels);

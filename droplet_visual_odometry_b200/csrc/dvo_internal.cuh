@@ -25,7 +25,7 @@ constexpr int kFastBoxW = 160;       // TMA box: 16 + tile + 16 (multiple of 16 
 constexpr int kFastBoxH = 40;
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
-constexpr int kSelectSmemBytes = 64 * 1024;
+constexpr int kSelectSmemBytes = 160 * 1024;   // k_select working array: 40960 candidates per level stay on chip
 constexpr int kRansacChunk = 128;    // RANSAC iterations solved+scored per launch group
 constexpr int kMaxModels = 10;
 
@@ -58,6 +58,8 @@ struct OrbBuffers {
     uint32_t* cand;          // [slots][candPerSlot]
     int* candCount;          // [slots][8]
     unsigned long long* pairs;   // [slots][candPerSlot]
+    uint32_t* selWork;       // [slots][candPerSlot]     k_select pass-1 working copy when a level does not fit in smem
+    uint32_t* selList;       // [slots][2*candPerSlot]   k_select stopper lists (left | right) per level
     uint32_t* finXY;         // [slots][finPerSlot]
     float* finResp;          // [slots][finPerSlot]
     int* finCount;           // [slots][8]

@@ -89,21 +89,27 @@ DVO_HD bool ring_has9(uint32_t m) {
 DVO_HD int imin(int a, int b) { return a < b ? a : b; }
 DVO_HD int imax(int a, int b) { return a > b ? a : b; }
 
-// Corner score of one pixel given centre value v and the 16 ring values; returns 0 if not a corner at threshold t,
-// else m-1 where m = max over the 16 arcs of max(min(d), min(-d)), d_k = v - p_k  (m > t  <=>  corner).
-// The arc maximum is evaluated pairwise (two 9-arcs share an 8-arc), starting the running bound at t.
-// (A straightforward 16x9 min/max double loop was miscompiled by nvcc 12.9 for sm_100a -- returned max(d) -- so this
-// formulation is deliberate; tests/test_gpu_* check it against the oracle on every level.)
-DVO_HD int fast_score16(int v, const int* p, int t) {
-    int d[25];
-    uint32_t brighter = 0, darker = 0;   // d > t  /  d < -t
+// Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
+DVO_HD bool fast_is_corner16(int v, const int* p, int t) {
+    uint32_t brighter = 0, darker = 0;   // d > t  /  d < -t  with d_k = v - p_k
+    const int lo = v - t, hi = v + t;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        d[k] = v - p[k];
-        brighter |= (uint32_t)(d[k] > t) << k;
-        darker |= (uint32_t)(d[k] < -t) << k;
+        brighter |= (uint32_t)(p[k] < lo) << k;
+        darker |= (uint32_t)(p[k] > hi) << k;
     }
-    if (!ring_has9(brighter) && !ring_has9(darker)) return 0;
+    return ring_has9(brighter) || ring_has9(darker);
+}
+
+// Score of a pixel already known to be a corner at threshold t: m-1 where m = max over the 16 arcs of
+// max(min(d), min(-d)), d_k = v - p_k  (m > t  <=>  corner).  The arc maximum is evaluated pairwise (two 9-arcs share an
+// 8-arc), starting the running bound at t.
+// (A straightforward 16x9 min/max double loop was miscompiled by nvcc 12.9 for sm_100a -- returned max(d) -- so this
+// formulation is deliberate; tests/test_gpu_* check it against the oracle on every level.)
+DVO_HD int fast_corner_score16(int v, const int* p, int t) {
+    int d[25];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = v - p[k];
 #pragma unroll
     for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
     int a0 = t;
@@ -125,6 +131,36 @@ DVO_HD int fast_score16(int v, const int* p, int t) {
         b0 = imin(b0, imax(b, d[k + 9]));
     }
     return -b0 - 1;
+}
+
+// Corner score of one pixel given centre value v and the 16 ring values; 0 if not a corner at threshold t.
+DVO_HD int fast_score16(int v, const int* p, int t) {
+    return fast_is_corner16(v, p, t) ? fast_corner_score16(v, p, t) : 0;
+}
+
+// Packed prefilter on 4 horizontally adjacent pixels (one per byte): c = centres, n/e/s/w = the compass ring points
+// (k = 0, 4, 8, 12) of each.  A 9-arc always holds two adjacent compass points, so a corner needs two adjacent compass
+// points with |v - p| > t; the byte test used here, (|v-p| >> 1) >= (t >> 1), is implied by it (never rejects a corner).
+// Returns 0x80 in every byte that may be a corner.
+DVO_HD uint32_t absdiff_u8x4(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vabsdiffu4(a, b);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        int x = (int)((a >> (8 * i)) & 0xFF) - (int)((b >> (8 * i)) & 0xFF);
+        r |= (uint32_t)(x < 0 ? -x : x) << (8 * i);
+    }
+    return r;
+#endif
+}
+DVO_HD uint32_t fast_prefilter_u8x4(uint32_t c, uint32_t n, uint32_t e, uint32_t s, uint32_t w, int t) {
+    const uint32_t bias = 0x01010101u * (uint32_t)(128 - (t >> 1));
+    uint32_t mn = (((absdiff_u8x4(c, n) >> 1) & 0x7f7f7f7fu) + bias);
+    uint32_t me = (((absdiff_u8x4(c, e) >> 1) & 0x7f7f7f7fu) + bias);
+    uint32_t ms = (((absdiff_u8x4(c, s) >> 1) & 0x7f7f7f7fu) + bias);
+    uint32_t mw = (((absdiff_u8x4(c, w) >> 1) & 0x7f7f7f7fu) + bias);
+    return (mn | ms) & (me | mw) & 0x80808080u;
 }
 
 // ---- A.3 Harris ------------------------------------------------------------------------------------------------

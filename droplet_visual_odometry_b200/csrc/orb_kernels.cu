@@ -68,6 +68,8 @@ template <bool kUseTma>
 __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
     __shared__ __align__(128) uint8_t raw[kFastBoxH * kFastBoxW];
     __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
+    __shared__ uint16_t list1[(kTileH + 2) * (kTileW + 2)], list2[(kTileH + 2) * (kTileW + 2)];
+    __shared__ int s_n1, s_n2;
     __shared__ __align__(8) unsigned long long bar;
 
     const int tile = blockIdx.x;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     const int tx = t % lv.tilesX, ty = t / lv.tilesX;
     const int x0 = tx * kTileW, y0 = ty * kTileH;
     const int slot = slot0 + blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     if (kUseTma) {
         if (tid == 0) {
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
                 "l"(reinterpret_cast<uint64_t>(&tm.pyr[L])), "r"(smem_u32(&bar)), "r"(x0 - kFastHaloL), "r"(y0 - 4), "r"(slot)
                 : "memory");
         }
+        for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
         // all threads wait for the bytes to land (phase 0)
         asm volatile(
             "{\n"
@@ -125,43 +129,96 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             }
             *reinterpret_cast<uint32_t*>(raw + ry * kFastBoxW + rw * 4) = v;
         }
-        __syncthreads();
+        for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
     }
+    __syncthreads();
 
-    // scores on the (tile + 1) ring: 130 x 34 positions, sx = x0-1+cx, sy = y0-1+cy
-    const int dxs[16] = DVO_FAST_DX, dys[16] = DVO_FAST_DY;
-    for (int i = tid; i < (kTileH + 2) * (kTileW + 2); i += 256) {
-        int cy = i / (kTileW + 2), cx = i % (kTileW + 2);
-        int sx = x0 - 1 + cx, sy = y0 - 1 + cy;
-        int score = 0;
-        if (sx >= 3 && sx < lv.w - 3 && sy >= 3 && sy < lv.h - 3) {
-            const uint8_t* c = raw + (cy + 3) * kFastBoxW + (cx + kFastHaloL - 1);
-            int v = *c;
-            // cheap reject: a 9-arc always contains one of every opposite pair
-            int d0 = v - c[3 * kFastBoxW], d8 = v - c[-3 * kFastBoxW];
-            int th = g.fastThreshold;
-            if (abs(d0) > th || abs(d8) > th) {
-                int p[16];
+    // ---- phase 1: packed prefilter, 4 adjacent positions per thread (quads aligned to 4 raw columns).
+    // Ring positions are 130 x 34 (tile + 1): raw rows 3..36, raw cols 15..144; a position is coded by its raw offset.
+    const int th = g.fastThreshold;
+    constexpr int kRowWords = kFastBoxW / 4;
+    constexpr int kQuadsX = 34, kQuadsY = kTileH + 2;
+    for (int q0 = 0; q0 < kQuadsX * kQuadsY; q0 += 256) {
+        const int q = q0 + tid;
+        uint32_t pass = 0;
+        int code0 = 0;
+        if (q < kQuadsX * kQuadsY) {
+            const int qy = q / kQuadsX, qx = q - qy * kQuadsX;
+            code0 = (qy + 3) * kFastBoxW + 12 + 4 * qx;
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + code0);
+            const uint32_t c = rp[0], lw = rp[-1], rw = rp[1];
+            const uint32_t up = rp[-3 * kRowWords], dn = rp[3 * kRowWords];
+            const uint32_t e = __byte_perm(c, rw, 0x6543), w = __byte_perm(lw, c, 0x4321);
+            pass = fast_prefilter_u8x4(c, up, e, dn, w, th);
+            // positions outside the ring columns or outside the level's FAST domain
+            const int sy = y0 - 4 + qy + 3;
+            if (sy < 3 || sy >= lv.h - 3) pass = 0;
+            const int sx0 = x0 - kFastHaloL + 12 + 4 * qx;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) p[k] = c[dys[k] * kFastBoxW + dxs[k]];
-                score = fast_score16(v, p, th);
-#ifdef DVO_DBG_FAST
-                if (L == 0 && slot == 0 && sx == 155 && sy == 31) {
-                    printf("DBG v=%d th=%d score=%d cx=%d cy=%d x0=%d y0=%d p:", v, th, score, cx, cy, x0, y0);
-                    for (int k = 0; k < 16; ++k) printf(" %d", p[k]);
-                    printf("\n");
-                }
-#endif
+            for (int k = 0; k < 4; ++k) {
+                const int rc = 12 + 4 * qx + k, sx = sx0 + k;
+                if (rc < 15 || rc > 144 || sx < 3 || sx >= lv.w - 3) pass &= ~(0x80u << (8 * k));
             }
         }
-        sc[cy * 136 + cx] = (uint8_t)score;
+        // warp-aggregated append
+        const int cnt = __popc(pass);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (pass & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(code0 + k);
+    }
+    __syncthreads();
+
+    // ---- phase 2: exact 16-point corner test on the survivors
+    const int dxs[16] = DVO_FAST_DX, dys[16] = DVO_FAST_DY;
+    const int n1 = s_n1;
+    for (int i0 = 0; i0 < n1; i0 += 256) {
+        const int i = i0 + tid;
+        bool corner = false;
+        int code = 0;
+        if (i < n1) {
+            code = list1[i];
+            const uint8_t* c = raw + code;
+            int pr[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
+            corner = fast_is_corner16(*c, pr, th);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, corner);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n2, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)code;
+    }
+    __syncthreads();
+
+    // ---- phase 3: scores of the corners
+    const int n2 = s_n2;
+    for (int i = tid; i < n2; i += 256) {
+        const int code = list2[i];
+        const uint8_t* c = raw + code;
+        int pr[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
+        const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
+        sc[(ry - 3) * 136 + (rx - 15)] = (uint8_t)fast_corner_score16(*c, pr, th);
     }
     __syncthreads();
 
     // NMS + write map + per-row survivor counts
     uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
     int* rowCount = b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5;
     const int border = 31;
     for (int r = warp; r < kTileH; r += 8) {
         int y = y0 + r;
@@ -345,35 +402,159 @@ __device__ __forceinline__ int harris_sums_warp(const uint8_t* img, int pitch, i
     return a;
 }
 
-__global__ void __launch_bounds__(256) k_select(OrbGeom g, OrbBuffers b, int slot0) {
+// Single-thread accessor (median-of-3 step).
+template <class T, class Key>
+struct OneAcc {
+    typedef T Item;
+    T* d;
+    __device__ __forceinline__ T get(int i) const { return d[i]; }
+    __device__ __forceinline__ void set(int i, T v) { d[i] = v; }
+    __device__ __forceinline__ static bool gt(T a, T b) { return Key::key(a) > Key::key(b); }
+};
+
+struct SelShared { int warpL[32], warpR[32]; int K; };
+
+// Whole-CTA accessor for the paired (data-parallel) form in select.cuh: each partition pass = two ballot sweeps
+// (stopper counts, then ranks + stopper lists + K) and K independent swaps.  Every thread runs the same scalar control
+// flow; element writes outside the swap phase are done by one thread / one warp and fenced with a CTA barrier.
+template <class T, class Key>
+struct BlockAcc {
+    typedef T Item;
+    T* d;
+    int n;
+    uint32_t* listL;     // scratch (global): left / right stopper positions by rank, >= n/2 + 2 entries each
+    uint32_t* listR;
+    SelShared* sh;
+    __device__ __forceinline__ T get(int i) const { return d[i]; }
+    __device__ __forceinline__ static bool gt(T a, T b) { return Key::key(a) > Key::key(b); }
+
+    __device__ void median_to_first(int result, int ia, int ib, int ic) {
+        if (threadIdx.x == 0) {
+            OneAcc<T, Key> one{d};
+            move_median_to_first(one, result, ia, ib, ic);
+        }
+        __syncthreads();
+    }
+    __device__ void sequential_tail(int first, int nth, int last, int depth) {
+        if (threadIdx.x < 32) {
+            WarpAcc<T, Key> w{d, n};
+            nth_element_replay_depth(w, first, nth, last, depth);
+        }
+        __syncthreads();
+    }
+    // kMode 0: Hoare pass against `ref` as pivot, returns the cut.  kMode 1: std::partition(x >= ref), returns the
+    // partition point.
+    template <int kMode>
+    __device__ int pair_swap(int first, int last, T ref) {
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nW = blockDim.x >> 5;
+        const int m = last - first;
+        const int seg = (((m + nW - 1) / nW) + 31) & ~31;
+        const int s0 = min(first + warp * seg, last), s1 = min(s0 + seg, last);
+        const auto kref = Key::key(ref);
+        int cL = 0, cR = 0;
+        for (int p = s0; p < s1; p += 32) {
+            const int i = p + lane;
+            bool l = false, r = false;
+            if (i < s1) {
+                const auto kx = Key::key(d[i]);
+                if (kMode == 0) { l = !(kx > kref); r = !(kref > kx); }
+                else { r = kx >= kref; l = !r; }
+            }
+            cL += __popc(__ballot_sync(0xffffffffu, l));
+            cR += __popc(__ballot_sync(0xffffffffu, r));
+        }
+        if (lane == 0) { sh->warpL[warp] = cL; sh->warpR[warp] = cR; }
+        if (tid == 0) sh->K = 0;
+        __syncthreads();
+        const int vL = lane < nW ? sh->warpL[lane] : 0, vR = lane < nW ? sh->warpR[lane] : 0;
+        int iL = vL, iR = vR;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, iL, o), c = __shfl_up_sync(0xffffffffu, iR, o);
+            if (lane >= o) { iL += a; iR += c; }
+        }
+        const int totalL = __shfl_sync(0xffffffffu, iL, 31), totalR = __shfl_sync(0xffffffffu, iR, 31);
+        int runL = __shfl_sync(0xffffffffu, iL - vL, warp), runR = __shfl_sync(0xffffffffu, iR - vR, warp);
+        const int cap = m / 2 + 1;
+        const unsigned lt = (1u << lane) - 1u;
+        int kc = 0;
+        for (int p = s0; p < s1; p += 32) {
+            const int i = p + lane;
+            bool l = false, r = false;
+            if (i < s1) {
+                const auto kx = Key::key(d[i]);
+                if (kMode == 0) { l = !(kx > kref); r = !(kref > kx); }
+                else { r = kx >= kref; l = !r; }
+            }
+            const unsigned ml = __ballot_sync(0xffffffffu, l), mr = __ballot_sync(0xffffffffu, r);
+            const int rl = runL + __popc(ml & lt), rrl = runR + __popc(mr & lt);
+            if (l) {
+                // pair rl exists iff more than rl right stoppers lie to the right of i
+                if (totalR - (rrl + (r ? 1 : 0)) >= rl + 1) ++kc;
+                if (rl <= cap) listL[rl] = (uint32_t)i;
+            }
+            if (r) {
+                const int rr = totalR - 1 - rrl;
+                if (rr <= cap) listR[rr] = (uint32_t)i;
+            }
+            runL += __popc(ml);
+            runR += __popc(mr);
+        }
+        kc = __reduce_add_sync(0xffffffffu, kc);
+        if (lane == 0 && kc) atomicAdd(&sh->K, kc);
+        __syncthreads();
+        const int K = sh->K;
+        for (int k = tid; k < K; k += blockDim.x) {
+            const int i = (int)listL[k], j = (int)listR[k];
+            const T x = d[i], y = d[j];
+            d[i] = y;
+            d[j] = x;
+        }
+        int res;
+        if (kMode == 0) {
+            const int lk = K < totalL ? (int)listL[K] : 0x7fffffff;
+            const int rk1 = K > 0 ? (int)listR[K - 1] : 0x7fffffff;
+            res = min(lk, rk1);
+        } else {
+            res = first + totalR;
+        }
+        __syncthreads();
+        return res;
+    }
+    __device__ int pair_swap_hoare(int first, int last, T pivot) { return pair_swap<0>(first, last, pivot); }
+    __device__ int pair_swap_ge(int first, int last, T boundary) { return pair_swap<1>(first, last, boundary); }
+};
+
+constexpr int kSelectThreads = 1024;
+constexpr int kSelectSeqTail = 64;    // ranges this short are finished by one warp running the scalar replay
+
+__global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ int s_n1, s_n2;
-    const int L = blockIdx.x;
-    const int slot = slot0 + blockIdx.y;
+    __shared__ SelShared sh;
+    const int L = blockIdx.y;                 // level-0 CTAs (the long ones) are dispatched first
+    const int slot = slot0 + blockIdx.x;
     const LevelGeom lv = g.lv[L];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t* cand = b.cand + (size_t)slot * g.candPerSlot + lv.candBase;
+    const uint32_t* cand = b.cand + (size_t)slot * g.candPerSlot + lv.candBase;
     unsigned long long* pairs = b.pairs + (size_t)slot * g.candPerSlot + lv.candBase;
-    int n = min(b.candCount[slot * kMaxLevels + L], lv.candCap);
+    uint32_t* listL = b.selList + ((size_t)slot * g.candPerSlot + lv.candBase) * 2;
+    uint32_t* listR = listL + lv.candCap;
+    const int n = min(b.candCount[slot * kMaxLevels + L], lv.candCap);
 
     // ---- pass 1: retainBest(2 * quota) on the FAST score, order-exact
-    const bool inSmem1 = (size_t)n * sizeof(uint32_t) <= (size_t)kSelectSmemBytes;
-    uint32_t* work1 = inSmem1 ? reinterpret_cast<uint32_t*>(s_dyn) : cand;
-    if (inSmem1) {
-        for (int i = tid; i < n; i += 256) work1[i] = cand[i];
-    }
+    const bool inSmem1 = (size_t)n * sizeof(uint32_t) <= (size_t)smemBytes;
+    uint32_t* work1 = inSmem1 ? reinterpret_cast<uint32_t*>(s_dyn) : b.selWork + (size_t)slot * g.candPerSlot + lv.candBase;
+    for (int i = tid; i < n; i += kSelectThreads) work1[i] = cand[i];
     __syncthreads();
-    if (warp == 0) {
-        WarpAcc<uint32_t, KeyScore> acc{work1, n};
-        int n1 = retain_best_replay(acc, n, 2 * lv.quota);
-        if (lane == 0) s_n1 = n1;
+    int n1;
+    {
+        BlockAcc<uint32_t, KeyScore> acc{work1, n, listL, listR, &sh};
+        n1 = retain_best_paired(acc, n, 2 * lv.quota, kSelectSeqTail);
     }
-    __syncthreads();
-    const int n1 = s_n1;
 
     // ---- Harris response of the survivors (un-blurred level)
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
-    for (int i = warp; i < n1; i += 8) {
+    for (int i = warp; i < n1; i += kSelectThreads / 32) {
         uint32_t c = work1[i];
         int x = c & 0xFFF, y = (c >> 12) & 0xFFF;
         int sb, sc_;
@@ -386,24 +567,22 @@ __global__ void __launch_bounds__(256) k_select(OrbGeom g, OrbBuffers b, int slo
     __syncthreads();   // pairs[] written with plain stores by this block, read back below after the barrier
 
     // ---- pass 2: retainBest(quota) on Harris, order-exact
-    const bool inSmem2 = (size_t)n1 * sizeof(unsigned long long) <= (size_t)kSelectSmemBytes;
+    const bool inSmem2 = (size_t)n1 * sizeof(unsigned long long) <= (size_t)smemBytes;
     unsigned long long* work2 = inSmem2 ? reinterpret_cast<unsigned long long*>(s_dyn) : pairs;
     if (inSmem2) {
-        for (int i = tid; i < n1; i += 256) work2[i] = pairs[i];
+        for (int i = tid; i < n1; i += kSelectThreads) work2[i] = pairs[i];
     }
     __syncthreads();
-    if (warp == 0) {
-        WarpAcc<unsigned long long, KeyHarris> acc{work2, n1};
-        int n2 = retain_best_replay(acc, n1, lv.quota);
-        if (lane == 0) s_n2 = n2;
+    int n2;
+    {
+        BlockAcc<unsigned long long, KeyHarris> acc{work2, n1, listL, listR, &sh};
+        n2 = retain_best_paired(acc, n1, lv.quota, kSelectSeqTail);
     }
-    __syncthreads();
-    int n2 = s_n2;
     int flags = 0;
     if (n2 > lv.finCap) { n2 = lv.finCap; flags |= 1; }
     uint32_t* finXY = b.finXY + (size_t)slot * g.finPerSlot + lv.finBase;
     float* finResp = b.finResp + (size_t)slot * g.finPerSlot + lv.finBase;
-    for (int i = tid; i < n2; i += 256) {
+    for (int i = tid; i < n2; i += kSelectThreads) {
         unsigned long long v = work2[i];
         finXY[i] = (uint32_t)(v & 0xFFFFFFu);
         finResp[i] = __uint_as_float((uint32_t)(v >> 32));
@@ -636,7 +815,7 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     { ProfScope ps_(PF_COMPACT, st); k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_compact", st);
-    { ProfScope ps_(PF_SELECT, st); k_select<<<dim3(g.nlevels, nSlots), 256, kSelectSmemBytes, st>>>(g, b, slot0); }
+    { ProfScope ps_(PF_SELECT, st); k_select<<<dim3(nSlots, g.nlevels), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes); }
     ++g_launches;
     debug_sync("k_select", st);
     { ProfScope ps_(PF_ANGLE, st); k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }

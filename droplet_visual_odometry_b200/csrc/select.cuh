@@ -129,10 +129,9 @@ DVO_HD int floor_log2(int n) {
     return r;
 }
 
+// introselect loop with the depth budget passed in (so a parallel front end can hand over mid-way)
 template <class Acc>
-DVO_HDN void nth_element_replay(Acc& a, int first, int nth, int last) {
-    if (first == last || nth == last) return;
-    int depth = floor_log2(last - first) * 2;
+DVO_HDN void nth_element_replay_depth(Acc& a, int first, int nth, int last, int depth) {
     while (last - first > 3) {
         if (depth == 0) {
             heap_select(a, first, nth + 1, last);
@@ -147,6 +146,12 @@ DVO_HDN void nth_element_replay(Acc& a, int first, int nth, int last) {
         else last = cut;
     }
     insertion_sort(a, first, last);
+}
+
+template <class Acc>
+DVO_HDN void nth_element_replay(Acc& a, int first, int nth, int last) {
+    if (first == last || nth == last) return;
+    nth_element_replay_depth(a, first, nth, last, floor_log2(last - first) * 2);
 }
 
 // std::partition(first, last, [b](x){ return x >= b; }) for bidirectional iterators; returns the partition point.
@@ -171,6 +176,50 @@ DVO_HDN int retain_best_replay(Acc& a, int count, int n_points) {
     nth_element_replay(a, 0, n_points - 1, count);
     typename Acc::Item boundary = a.get(n_points - 1);
     return partition_ge(a, n_points, count, boundary);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Data-parallel form of the same two algorithms.
+//
+// Both partition loops (Hoare's unguarded partition inside introselect, and the bidirectional std::partition) do the
+// same thing: walk a left cursor to the next "left stopper", a right cursor to the next "right stopper", swap, repeat
+// while left < right.  A swapped position is never looked at again in that pass, so the swaps are exactly
+//     (L[k], R[k])  for k = 0 .. K-1,   K = #{k : L[k] < R[k]},
+// L = left stoppers in ascending index order, R = right stoppers in descending index order, both taken on the array as
+// it was BEFORE the pass.  Hoare:  left stopper = !(x > pivot), right stopper = !(pivot > x), cut = min(L[K], R[K-1]).
+// std::partition(pred = x >= b):  left stopper = !pred, right stopper = pred, result = first + #right stoppers.
+// That turns each pass into flags + prefix sums + K independent swaps, which a whole CTA does at once
+// (orb_kernels.cu: BlockAcc); the introselect control flow around it stays the scalar one below.  tests/hostsim checks
+// this formulation, with a plain-loop accessor, against the real std::nth_element / std::partition.
+//
+// Additional accessor contract for the paired form:
+//   void median_to_first(int result, int ia, int ib, int ic)   -- move_median_to_first, then make writes visible
+//   int  pair_swap_hoare(int first, int last, Item pivot)      -- returns the cut
+//   int  pair_swap_ge(int first, int last, Item boundary)      -- returns the partition point
+//   void sequential_tail(int first, int nth, int last, int depth) -- nth_element_replay_depth on one lane/warp + barrier
+template <class Acc>
+DVO_HDN void nth_element_paired(Acc& a, int first, int nth, int last, int seq_tail) {
+    if (first == last || nth == last) return;
+    int depth = floor_log2(last - first) * 2;
+    while (last - first > 3) {
+        if (depth == 0 || last - first <= seq_tail) break;
+        --depth;
+        int mid = first + (last - first) / 2;
+        a.median_to_first(first, first + 1, mid, last - 1);
+        int cut = a.pair_swap_hoare(first + 1, last, a.get(first));
+        if (cut <= nth) first = cut;
+        else last = cut;
+    }
+    a.sequential_tail(first, nth, last, depth);
+}
+
+template <class Acc>
+DVO_HDN int retain_best_paired(Acc& a, int count, int n_points, int seq_tail) {
+    if (!(n_points >= 0 && count > n_points)) return count;
+    if (n_points == 0) return 0;
+    nth_element_paired(a, 0, n_points - 1, count, seq_tail);
+    typename Acc::Item boundary = a.get(n_points - 1);
+    return a.pair_swap_ge(n_points, count, boundary);
 }
 
 }  // namespace dvo

@@ -24,7 +24,45 @@ struct HostAcc {
     int scan_down_lt(int first, int last, Item b) { while (first != last && !(d[last].r >= b.r)) --last; return last; }
 };
 
+// Plain-loop accessor for the paired (data-parallel) formulation of select.cuh: builds the stopper lists explicitly.
+struct HostPairAcc : HostAcc {
+    template <class IsL, class IsR>
+    int pair_swap(int first, int last, IsL isL, IsR isR, int* cut_hoare) {
+        std::vector<int> L, R;
+        for (int i = first; i < last; ++i) if (isL(d[i])) L.push_back(i);
+        for (int i = last - 1; i >= first; --i) if (isR(d[i])) R.push_back(i);
+        size_t K = 0;
+        while (K < L.size() && K < R.size() && L[K] < R[K]) ++K;
+        for (size_t k = 0; k < K; ++k) std::swap(d[L[k]], d[R[k]]);
+        int lk = K < L.size() ? L[K] : 0x7fffffff, rk1 = K > 0 ? R[K - 1] : 0x7fffffff;
+        *cut_hoare = std::min(lk, rk1);
+        return (int)R.size();
+    }
+    void median_to_first(int result, int ia, int ib, int ic) { move_median_to_first(*this, result, ia, ib, ic); }
+    int pair_swap_hoare(int first, int last, Item pivot) {
+        int cut;
+        pair_swap(first, last, [&](Item x) { return !gt(x, pivot); }, [&](Item x) { return !gt(pivot, x); }, &cut);
+        return cut;
+    }
+    int pair_swap_ge(int first, int last, Item b) {
+        int cut;
+        int nr = pair_swap(first, last, [&](Item x) { return !(x.r >= b.r); }, [&](Item x) { return x.r >= b.r; }, &cut);
+        return first + nr;
+    }
+    void sequential_tail(int first, int nth, int last, int depth) { nth_element_replay_depth(*this, first, nth, last, depth); }
+};
+
 extern "C" {
+
+int hs_retain_best_paired(const float* resp, int count, int n_points, int seq_tail, int32_t* out_idx) {
+    std::vector<HostItem> v(count);
+    for (int i = 0; i < count; ++i) v[i] = HostItem{resp[i], i};
+    HostPairAcc acc;
+    acc.d = v.data();
+    int k = retain_best_paired(acc, count, n_points, seq_tail);
+    for (int i = 0; i < k; ++i) out_idx[i] = v[i].idx;
+    return k;
+}
 
 int hs_retain_best(const float* resp, int count, int n_points, int32_t* out_idx) {
     std::vector<HostItem> v(count);
@@ -59,6 +97,31 @@ void hs_fast_score_map(const uint8_t* img, int w, int h, int pitch, int t, uint8
             for (int k = 0; k < 16; ++k) p[k] = img[(y + dy[k]) * pitch + x + dx[k]];
             out[y * w + x] = (uint8_t)fast_score16(img[y * pitch + x], p, t);
         }
+}
+
+// number of corners (fast_score16 > 0) the packed prefilter would reject: must be 0.  Also returns the pass count.
+int hs_fast_prefilter_check(const uint8_t* img, int w, int h, int pitch, int t, int* passed) {
+    const int dx[16] = DVO_FAST_DX, dy[16] = DVO_FAST_DY;
+    int missed = 0, np_ = 0;
+    for (int y = 3; y < h - 3; ++y)
+        for (int x = 4; x + 4 < w - 3; x += 4) {
+            auto quad = [&](int yy, int xx) {
+                uint32_t r = 0;
+                for (int k = 0; k < 4; ++k) r |= (uint32_t)img[yy * pitch + xx + k] << (8 * k);
+                return r;
+            };
+            uint32_t pass = fast_prefilter_u8x4(quad(y, x), quad(y - 3, x), quad(y, x + 3), quad(y + 3, x), quad(y, x - 3), t);
+            for (int k = 0; k < 4; ++k) {
+                int p[16];
+                for (int j = 0; j < 16; ++j) p[j] = img[(y + dy[j]) * pitch + x + k + dx[j]];
+                bool corner = fast_score16(img[y * pitch + x + k], p, t) > 0;
+                bool ps = (pass >> (8 * k + 7)) & 1;
+                np_ += ps;
+                if (corner && !ps) ++missed;
+            }
+        }
+    *passed = np_;
+    return missed;
 }
 
 float hs_harris(int a, int b, int c) { return harris_from_sums(a, b, c); }

@@ -26,6 +26,29 @@ def test_retain_best_replay_matches_libstdcpp(hostsim):
         assert m == len(ref) and np.array_equal(out[:m], ref)
 
 
+def test_retain_best_paired_formulation_matches_libstdcpp(hostsim):
+    """the data-parallel (stopper-list) form of nth_element + partition that k_select runs, vs the real std:: calls"""
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        n = int(rng.integers(1, 6000))
+        k = int(rng.integers(0, n + 5))
+        kind = trial % 4
+        if kind == 0:
+            resp = rng.integers(20, 60, n).astype(np.float32)
+        elif kind == 1:
+            resp = rng.random(n).astype(np.float32)
+        elif kind == 2:
+            resp = np.sort(rng.integers(20, 255, n)).astype(np.float32)[::(-1 if trial % 8 < 4 else 1)].copy()
+        else:
+            resp = np.full(n, 33.0, np.float32)
+            resp[rng.integers(0, n, max(1, n // 50))] = 90.0
+        ref = O.retain_best(resp, k)
+        out = np.empty(n + 1, np.int32)
+        for tail in (0, 3, 64, 100000):
+            m = hostsim.hs_retain_best_paired(ptr(resp), n, k, tail, ptr(out))
+            assert m == len(ref) and np.array_equal(out[:m], ref), (trial, n, k, tail)
+
+
 def test_heap_select_fallback(hostsim):
     rng = np.random.default_rng(1)
     for trial in range(100):
@@ -40,6 +63,19 @@ def test_fast_score_map(hostsim, golden):
     out = np.zeros_like(img)
     hostsim.hs_fast_score_map(ptr(img), 320, 200, 320, 20, ptr(out))
     assert np.array_equal(out, O.fast_score_map(img))
+
+
+def test_fast_packed_prefilter_never_rejects_a_corner(hostsim, golden):
+    import ctypes
+    rng = np.random.default_rng(5)
+    imgs = [np.ascontiguousarray(golden["frame0"][:240, :320]), rng.integers(0, 256, (120, 160)).astype(np.uint8),
+            (rng.integers(0, 2, (120, 160)) * 41 + 100).astype(np.uint8)]
+    for img in imgs:
+        for t in (1, 20, 21, 60):
+            passed = ctypes.c_int()
+            h, w = img.shape
+            assert hostsim.hs_fast_prefilter_check(ptr(img), w, h, w, t, ctypes.byref(passed)) == 0
+            assert passed.value < img.size
 
 
 def test_fast_atan2_and_harris(hostsim):
