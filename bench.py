@@ -260,6 +260,9 @@ def run_b200(a):
     value = world * npairs / (ms / 1e3)
     host_poses = poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec].cpu().numpy().view(POSE_DTYPE)
     ok_frac = float(np.mean(host_poses["status"] == 0))
+    pair_stats = {"ransac_iters_median": float(np.median(host_poses["ransac_iters"])), "ransac_iters_max": int(host_poses["ransac_iters"].max()),
+                  "matches_median": float(np.median(host_poses["n_matches"])),
+                  "inlier_ratio_median": float(np.median(host_poses["n_inliers"] / np.maximum(host_poses["n_matches"], 1)))}
 
     # ---- end to end through the public API: pinned host frames in, pose records out, every step
     e2e_frames = frames[W_steps * B:(W_steps + K_steps) * B + 1].cpu().pin_memory()
@@ -328,8 +331,8 @@ def run_b200(a):
             achieved = alg * groups / (dms * 1e-3) / 1e9
         else:
             # not a streaming kernel: its algorithmic HBM bytes are the records it must read and write per batch
-            per_pair = {"k_nn": 2 * nkp * 32 * 2 + nkp * 16, "k_select": total_px // 256 * 4, "k_solve": 128 * 10 * 72,
-                        "k_score": nkp * 32 + 128 * 10 * 76, "k_cheirality": nkp * 33}.get(dom, nkp * 32)
+            per_pair = {"k_nn": 2 * nkp * 32 * 2 + nkp * 16, "k_select": total_px // 256 * 4, "k_ransac": nkp * 33,
+                        "k_cheirality": nkp * 33}.get(dom, nkp * 32)
             alg = per_pair * B
             achieved = alg * dcnt / (dms * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
@@ -364,7 +367,7 @@ def run_b200(a):
                           "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
                               B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
                           "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
-                          "pairs_ok_fraction": ok_frac},
+                          "pairs_ok_fraction": ok_frac, "pair_stats": pair_stats},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height, "d2h_bytes_per_step": B * rec},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)

@@ -260,7 +260,6 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     while (pg.sortCap < g.maxkp) pg.sortCap <<= 1;
     pg.matcher = cfg->matcher;
     pg.maxIters = cfg->ransac_max_iters;
-    pg.nChunks = (pg.maxIters + kRansacChunk - 1) / kRansacChunk;
     pg.prob = cfg->ransac_prob;
     pg.threshold = cfg->ransac_threshold;
     pg.distThresh = cfg->distance_thresh;
@@ -275,9 +274,6 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     DA(pb.ptsCur, P * M * 2);
     DA(pb.normPts, P * M * 4);
     DA(pb.samples, P * (size_t)pg.maxIters * 5);
-    DA(pb.models, P * (size_t)kRansacChunk * kMaxModels * 9);
-    DA(pb.modelCount, P * (size_t)kRansacChunk);
-    DA(pb.modelGood, P * (size_t)kRansacChunk * kMaxModels);
     DA(pb.ransacState, P * 8);
     DA(pb.bestE, P * 9);
     DA(pb.ransacMask, P * M);
@@ -556,7 +552,7 @@ int dvo_profile_collect(double* ms, int* count, int n) {
 }
 const char* dvo_profile_name(int id) {
     static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_compact", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
-                                          "k_match_sort", "k_solve", "k_score", "k_replay", "k_pose_prep", "k_cheirality", "k_pose_final"};
+                                          "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final"};
     return (id >= 0 && id < PF_COUNT) ? names[id] : "";
 }
 

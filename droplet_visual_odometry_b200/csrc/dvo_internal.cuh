@@ -26,7 +26,6 @@ constexpr int kFastBoxH = 40;
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
 constexpr int kSelectSmemBytes = 160 * 1024;   // k_select working array: 40960 candidates per level stay on chip
-constexpr int kRansacChunk = 128;    // RANSAC iterations solved+scored per launch group
 constexpr int kMaxModels = 10;
 
 struct LevelGeom {
@@ -86,7 +85,6 @@ struct PairGeom {
     int sortCap;          // power of two >= maxkp
     int matcher;          // 0 crosscheck, 1 knn ratio + reverse check
     int maxIters;
-    int nChunks;
     double prob, threshold, distThresh;
     float ratio;
 };
@@ -105,10 +103,7 @@ struct PairBuffers {
     float* ptsCur;        // [pairs][maxkp][2]
     double* normPts;      // [pairs][maxkp][4]           x1 y1 x2 y2 normalised
     int* samples;         // [pairs][maxIters][5]
-    double* models;       // [pairs][chunk][10][9]
-    int* modelCount;      // [pairs][chunk]
-    int* modelGood;       // [pairs][chunk][10]
-    int* ransacState;     // [pairs][8]: maxGood, niters, done, bestIter, bestModel, itersRun, modelsScored, hasBest
+    int* ransacState;     // [pairs][8]: maxGood, niters, done, bestIter, bestModel, rng lo, rng hi, hasBest
     double* bestE;        // [pairs][9]
     uint8_t* ransacMask;  // [pairs][maxkp]
     uint8_t* poseMask;    // [pairs][maxkp]
@@ -117,8 +112,8 @@ struct PairBuffers {
 };
 
 // ---- per-kernel CUDA-event profiler (bench.py's roofline pass; off by default, zero cost when off)
-enum ProfId { PF_PYR = 0, PF_FAST, PF_COMPACT, PF_SELECT, PF_ANGLE, PF_BLUR, PF_BRIEF, PF_NN, PF_SORT, PF_SOLVE, PF_SCORE, PF_REPLAY,
-              PF_POSE_PREP, PF_CHEIRALITY, PF_POSE_FINAL, PF_COUNT };
+enum ProfId { PF_PYR = 0, PF_FAST, PF_COMPACT, PF_SELECT, PF_ANGLE, PF_BLUR, PF_BRIEF, PF_NN, PF_SORT, PF_RANSAC,
+              PF_CHEIRALITY, PF_POSE_FINAL, PF_COUNT };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 struct ProfScope {

@@ -230,6 +230,26 @@ DVO_HD float sampson_error_f32(const double* E, double x1, double y1, double x2,
     return (float)(dmul(x2tEx1, x2tEx1) / den);
 }
 
+// Same decision as `sampson_error_f32(...) <= t32`, with the division skipped when the ratio is not within 1e-6 of the
+// threshold: tlo = (double)t32 * (1 - 1e-6), thi = (double)t32 * (1 + 1e-6).  float rounding is monotonic and t32 is a
+// float, so num/den <= tlo implies (float)(num/den) <= t32, and num/den >= thi (> t32's upper rounding midpoint, relative
+// 6e-8) implies (float)(num/den) > t32; anything in between, and every non-finite case, takes the exact path.
+DVO_HD bool sampson_inlier(const double* E, double x1, double y1, double x2, double y2, float t32, double tlo, double thi) {
+    double ex0 = dadd(dadd(dmul(E[0], x1), dmul(E[1], y1)), E[2]);
+    double ex1 = dadd(dadd(dmul(E[3], x1), dmul(E[4], y1)), E[5]);
+    double ex2 = dadd(dadd(dmul(E[6], x1), dmul(E[7], y1)), E[8]);
+    double et0 = dadd(dadd(dmul(E[0], x2), dmul(E[3], y2)), E[6]);
+    double et1 = dadd(dadd(dmul(E[1], x2), dmul(E[4], y2)), E[7]);
+    double x2tEx1 = dadd(dadd(dmul(x2, ex0), dmul(y2, ex1)), ex2);
+    double den = dadd(dadd(dadd(dmul(ex0, ex0), dmul(ex1, ex1)), dmul(et0, et0)), dmul(et1, et1));
+    double num = dmul(x2tEx1, x2tEx1);
+    if (den > 0.0 && den < 1e300 && num < 1e300) {
+        if (num <= dmul(den, tlo)) return true;
+        if (num >= dmul(den, thi)) return false;
+    }
+    return (float)(num / den) <= t32;
+}
+
 // ---- small dense linear algebra ------------------------------------------------------------------------------------
 // One-sided (Hestenes) Jacobi on the columns of an NxN matrix A (row-major, overwritten by U*Sigma); V accumulates the
 // right singular vectors as columns.
@@ -361,12 +381,16 @@ DVO_HD int cubic_index(int q, int l) {
     return T[q][l];
 }
 
-DVO_HDN void poly_mul11(const double* a, const double* b, double* out10, double sign) {
+DVO_HD void poly_mul11(const double* a, const double* b, double* out10, double sign) {
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) out10[quad_index(i, j)] += sign * a[i] * b[j];
 }
-DVO_HDN void poly_mul21(const double* a10, const double* b, double* out20, double sign) {
+DVO_HD void poly_mul21(const double* a10, const double* b, double* out20, double sign) {
+#pragma unroll
     for (int i = 0; i < 10; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) out20[cubic_index(i, j)] += sign * a10[i] * b[j];
 }
 

@@ -645,9 +645,16 @@ __global__ void __launch_bounds__(256) k_angle_pack(OrbGeom g, OrbBuffers b, int
 }
 
 // =========================================================================================== A.6 blur
+// Row pass straight from global memory (aligned 32-bit words, four outputs per thread), float rows in shared memory,
+// column pass with 128-bit shared loads and one 32-bit store per four pixels.
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return max(0, min(p, n - 1));
+}
+
 __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0) {
-    __shared__ uint8_t raw[(kTileH + 6) * 136];
-    __shared__ float hrow[(kTileH + 6) * kTileW];
+    __shared__ __align__(16) float hrow[(kTileH + 6) * kTileW];
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
     const int tile = blockIdx.x;
@@ -659,52 +666,64 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
     const int tid = threadIdx.x;
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
     uint8_t* out = b.blur + (size_t)slot * g.slotStride + lv.off;
-    // stage tile + 3-px halo with BORDER_REFLECT_101
-    for (int i = tid; i < (kTileH + 6) * (kTileW + 6); i += 256) {
-        int ry = i / (kTileW + 6), rx = i % (kTileW + 6);
-        int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
-        if (gy < 0) gy = -gy;
-        if (gy >= lv.h) gy = 2 * lv.h - 2 - gy;
-        if (gx < 0) gx = -gx;
-        if (gx >= lv.w) gx = 2 * lv.w - 2 - gx;
-        gy = max(0, min(gy, lv.h - 1));
-        gx = max(0, min(gx, lv.w - 1));
-        raw[ry * 136 + rx] = img[(size_t)gy * lv.pitch + gx];
-    }
-    __syncthreads();
-    // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6
-    for (int i = tid; i < (kTileH + 6) * kTileW; i += 256) {
-        int ry = i / kTileW, x = i % kTileW;
-        const uint8_t* p = raw + ry * 136 + x;
-        float s = fmul(k0, (float)p[0]);
-        s = ffma(k1, (float)p[1], s);
-        s = ffma(k2, (float)p[2], s);
-        s = ffma(k3, (float)p[3], s);
-        s = ffma(k2, (float)p[4], s);
-        s = ffma(k1, (float)p[5], s);
-        s = ffma(k0, (float)p[6], s);
-        hrow[i] = s;
+    // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6  (BORDER_REFLECT_101 on both axes)
+    for (int i = tid; i < (kTileH + 6) * (kTileW / 4); i += 256) {
+        const int ry = i / (kTileW / 4), xq = (i - ry * (kTileW / 4)) * 4;
+        const int gx = x0 + xq;
+        if (gx >= lv.w) continue;             // whole quad outside the level: never read by the column pass
+        const int gy = reflect101(y0 - 3 + ry, lv.h);
+        const uint8_t* rowp = img + (size_t)gy * lv.pitch;
+        float p[10];
+        if (gx >= 4 && gx + 7 < lv.w) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp + gx);
+            const uint32_t w0 = __ldg(wp - 1), w1 = __ldg(wp), w2 = __ldg(wp + 1);
+            p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
+            p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
+            p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) p[k] = (float)rowp[reflect101(gx - 3 + k, lv.w)];
+        }
+        float4 o;
+        float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s = fmul(k0, p[k]);
+            s = ffma(k1, p[k + 1], s);
+            s = ffma(k2, p[k + 2], s);
+            s = ffma(k3, p[k + 3], s);
+            s = ffma(k2, p[k + 4], s);
+            s = ffma(k1, p[k + 5], s);
+            s = ffma(k0, p[k + 6], s);
+            ov[k] = s;
+        }
+        *reinterpret_cast<float4*>(hrow + ry * kTileW + xq) = o;
     }
     __syncthreads();
     // column pass, 4 pixels per thread
     for (int i = tid; i < kTileH * (kTileW / 4); i += 256) {
-        int r = i / (kTileW / 4), xq = (i % (kTileW / 4)) * 4;
-        int y = y0 + r;
-        if (y >= lv.h) continue;
+        const int r = i / (kTileW / 4), xq = (i - r * (kTileW / 4)) * 4;
+        const int y = y0 + r, x = x0 + xq;
+        if (y >= lv.h || x >= lv.w) continue;
+        const float* h = hrow + (r + 3) * kTileW + xq;
+        const float4 c = *reinterpret_cast<const float4*>(h);
+        const float4 u1 = *reinterpret_cast<const float4*>(h - kTileW), d1 = *reinterpret_cast<const float4*>(h + kTileW);
+        const float4 u2 = *reinterpret_cast<const float4*>(h - 2 * kTileW), d2 = *reinterpret_cast<const float4*>(h + 2 * kTileW);
+        const float4 u3 = *reinterpret_cast<const float4*>(h - 3 * kTileW), d3 = *reinterpret_cast<const float4*>(h + 3 * kTileW);
         uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float* h = hrow + (r + 3) * kTileW + xq + k;
-            float s = fmul(k3, h[0]);
-            s = ffma(k2, fadd(h[kTileW], h[-kTileW]), s);
-            s = ffma(k1, fadd(h[2 * kTileW], h[-2 * kTileW]), s);
-            s = ffma(k0, fadd(h[3 * kTileW], h[-3 * kTileW]), s);
-            int v = __float2int_rn(s);
-            v = max(0, min(255, v));
-            word |= (uint32_t)v << (8 * k);
+#define DVO_BLUR_COL(F, SH)                                        \
+        {                                                          \
+            float s = fmul(k3, c.F);                               \
+            s = ffma(k2, fadd(d1.F, u1.F), s);                     \
+            s = ffma(k1, fadd(d2.F, u2.F), s);                     \
+            s = ffma(k0, fadd(d3.F, u3.F), s);                     \
+            int v = __float2int_rn(s);                             \
+            v = max(0, min(255, v));                               \
+            word |= (uint32_t)v << SH;                             \
         }
-        int x = x0 + xq;
-        if (x < lv.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)y * lv.pitch + x) = word;
+        DVO_BLUR_COL(x, 0) DVO_BLUR_COL(y, 8) DVO_BLUR_COL(z, 16) DVO_BLUR_COL(w, 24)
+#undef DVO_BLUR_COL
+        *reinterpret_cast<uint32_t*>(out + (size_t)y * lv.pitch + x) = word;
     }
 }
 

@@ -4,14 +4,13 @@
 //
 //   k_nn            A.8  tiled XOR+POPC nearest neighbour (both directions in one launch; 2-NN distance for the ratio test)
 //   k_match_sort    A.8  cross-check / ratio+reverse check, bitonic sort on (distance, queryIdx), point gather, K-normalise
-//   k_solve         A.9  per chunk of 128 RANSAC iterations: cv::RNG sample stream (lane 0) + one 5-point solve per thread
-//   k_score         A.9  Sampson error of every match against every model, warp-reduced inlier counts
-//   k_replay        A.9  cv2's strict-'>' update and adaptive stop rule, replayed in order
-//   k_pose_prep     A.9/A.10  final RANSAC mask, SVD of E -> R1, R2, t
+//   k_ransac        A.9/A.10  one CTA per pair: cv::RNG sample stream, 5-point solves (one per 16-lane group), Sampson scoring,
+//                        cv2's strict-'>' update + adaptive stop replayed in order; final mask, SVD of E -> R1, R2, t
 //   k_cheirality    A.10 per point x 4 candidates DLT triangulation + cheirality votes
 //   k_pose_final    A.10 '>=' cascade, masks, dvo_pose record
 #include "dvo_internal.cuh"
 #include "mathcore.cuh"
+#include "fivepoint_group.cuh"
 
 namespace dvo {
 void debug_sync(const char* name, cudaStream_t st);
@@ -20,21 +19,27 @@ void debug_sync(const char* name, cudaStream_t st);
 enum { RS_MAXGOOD = 0, RS_NITERS = 1, RS_DONE = 2, RS_BESTITER = 3, RS_BESTMODEL = 4, RS_RNG_LO = 5, RS_RNG_HI = 6, RS_HASBEST = 7 };
 
 // ================================================================================================ matching
+// Every Hamming distance is computed once: the thread that owns query i keeps the row minimum (and runner-up) in
+// registers, and the same distance feeds the column minimum through one redux.sync per (warp, train descriptor) on the
+// packed key (distance << 16 | queryIdx) -- so ties go to the lowest index on both sides, as cv2's batchDistance does.
+// Column keys are merged warp -> CTA (shared atomicMin) -> pair (global atomicMin); the launcher presets them to ~0.
 __global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0) {
     __shared__ __align__(16) uint32_t tile[128 * 8];
-    const int pi = blockIdx.z;
-    const int dir = blockIdx.y;
-    const int slotA = slotA0 + pi + (dir ? 1 : 0);
-    const int slotB = slotA0 + pi + (dir ? 0 : 1);
+    __shared__ uint32_t colmin[128];
+    const int pi = blockIdx.y;
+    const int slotA = slotA0 + pi, slotB = slotA + 1;
     const int pair = pair0 + pi;
     const int nA = min(ob.featCount[slotA], pg.maxkp), nB = min(ob.featCount[slotB], pg.maxkp);
     if (blockIdx.x * 128 >= nA) return;
     const int i = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < nA;
     const uint32_t* dA = reinterpret_cast<const uint32_t*>(ob.featDesc + (size_t)slotA * og.maxkp * 32);
     const uint32_t* dB = reinterpret_cast<const uint32_t*>(ob.featDesc + (size_t)slotB * og.maxkp * 32);
+    uint32_t* colKey = reinterpret_cast<uint32_t*>(pb.nnIdx + ((size_t)pair * 2 + 1) * pg.maxkp);
     uint32_t q[8];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) q[w] = (i < nA) ? dA[(size_t)i * 8 + w] : 0u;
+    for (int w = 0; w < 8; ++w) q[w] = valid ? dA[(size_t)i * 8 + w] : 0u;
     int best = 0x7fffffff, bestIdx = -1, second = 0x7fffffff;
     for (int j0 = 0; j0 < nB; j0 += 128) {
         __syncthreads();
@@ -45,22 +50,34 @@ __global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom 
             if (j < nB) val = reinterpret_cast<const uint4*>(dB)[(size_t)j * 2 + (v & 1)];
             reinterpret_cast<uint4*>(tile)[v] = val;
         }
+        colmin[threadIdx.x] = 0xFFFFFFFFu;
         __syncthreads();
         const int lim = min(128, nB - j0);
+        uint32_t mycol = 0xFFFFFFFFu;        // lane l: this warp's minimum for column (j & ~31) + l
         for (int j = 0; j < lim; ++j) {
             const uint4 t0 = reinterpret_cast<const uint4*>(tile)[j * 2];
             const uint4 t1 = reinterpret_cast<const uint4*>(tile)[j * 2 + 1];
-            int d = __popc(q[0] ^ t0.x) + __popc(q[1] ^ t0.y) + __popc(q[2] ^ t0.z) + __popc(q[3] ^ t0.w) +
-                    __popc(q[4] ^ t1.x) + __popc(q[5] ^ t1.y) + __popc(q[6] ^ t1.z) + __popc(q[7] ^ t1.w);
+            const int d = __popc(q[0] ^ t0.x) + __popc(q[1] ^ t0.y) + __popc(q[2] ^ t0.z) + __popc(q[3] ^ t0.w) +
+                          __popc(q[4] ^ t1.x) + __popc(q[5] ^ t1.y) + __popc(q[6] ^ t1.z) + __popc(q[7] ^ t1.w);
             if (d < best) { second = best; best = d; bestIdx = j0 + j; }
             else if (d < second) second = d;
+            const uint32_t key = valid ? (((uint32_t)d << 16) | (uint32_t)i) : 0xFFFFFFFFu;
+            const uint32_t m = __reduce_min_sync(0xffffffffu, key);
+            if (lane == (j & 31)) mycol = m;
+            if ((j & 31) == 31 || j == lim - 1) {
+                const int jj = (j & ~31) + lane;
+                if (jj <= j) atomicMin(&colmin[jj], mycol);
+                mycol = 0xFFFFFFFFu;
+            }
         }
+        __syncthreads();
+        if (threadIdx.x < lim) atomicMin(&colKey[j0 + threadIdx.x], colmin[threadIdx.x]);
     }
-    if (i < nA) {
-        size_t o = ((size_t)pair * 2 + dir) * pg.maxkp + i;
+    if (valid) {
+        size_t o = (size_t)pair * 2 * pg.maxkp + i;
         pb.nnIdx[o] = bestIdx;
         pb.nnDist[o] = best;
-        if (dir == 0) pb.nn2Dist[(size_t)pair * pg.maxkp + i] = second;
+        pb.nn2Dist[(size_t)pair * pg.maxkp + i] = second;
     }
 }
 
@@ -75,7 +92,7 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
     const int tid = threadIdx.x;
     const int* fwd = pb.nnIdx + ((size_t)pair * 2 + 0) * pg.maxkp;
     const int* fwdD = pb.nnDist + ((size_t)pair * 2 + 0) * pg.maxkp;
-    const int* bwd = pb.nnIdx + ((size_t)pair * 2 + 1) * pg.maxkp;
+    const uint32_t* bwdKey = reinterpret_cast<const uint32_t*>(pb.nnIdx + ((size_t)pair * 2 + 1) * pg.maxkp);   // d << 16 | queryIdx
     const int* d2 = pb.nn2Dist + (size_t)pair * pg.maxkp;
     if (tid == 0) s_count = 0;
     __syncthreads();
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
         uint32_t key = 0xFFFFFFFFu;
         if (i < nA && nB > 0) {
             int j = fwd[i];
-            bool ok = j >= 0 && bwd[j] == i;
+            bool ok = j >= 0 && (int)(bwdKey[j] & 0xFFFFu) == i;
             if (pg.matcher == DVO_MATCH_KNN_RATIO) {
                 // knnMatch returns < 2 neighbours when the train set has one descriptor: the reference's unpacking needs two
                 ok = ok && nB >= 2 && ((double)fwdD[i] < (double)pg.ratio * (double)d2[i]);
@@ -141,142 +158,157 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
 }
 
 // ================================================================================================ RANSAC
-__global__ void __launch_bounds__(kRansacChunk) k_solve(PairGeom pg, PairBuffers pb, int pair0, int chunk) {
-    __shared__ int s_samples[kRansacChunk][5];
+// One CTA per frame pair runs cv2's whole findEssentialMat loop: per chunk of kRansacGroups iterations
+//   thread 0: cv::RNG sample stream (5 distinct positions, single-index redraw)
+//   16-lane groups: one 5-point solve each (fivepoint_group.cuh), models into shared memory
+//   warps: Sampson error of every match against every model, warp-reduced inlier counts
+//   thread 0: cv2's strict-'>' update + adaptive stop rule, in iteration order (speculated iterations past the stop are
+//             discarded, so E, mask and iteration count are the ones the sequential loop produces)
+// then the final mask and the SVD of E for recoverPose.  No launch is spent on pairs that have already stopped.
+constexpr int kRansacGroups = 16;
+constexpr int kRansacThreads = kRansacGroups * kGroupLanes;
+
+struct RansacShared {
+    SolveScratch scratch[kRansacGroups];
+    double models[kRansacGroups][kMaxModels][9];
+    double bestE[9];
+    unsigned long long rng;
+    int samples[kRansacGroups][5];
+    int modelCount[kRansacGroups];
+    int modelGood[kRansacGroups][kMaxModels];
+    int maxGood, niters, done, it0, bestIter, bestModel, hasBest, cnt;
+};
+
+__global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
+    __shared__ RansacShared sh;
     const int pair = pair0 + blockIdx.x;
     int* rs = pb.ransacState + pair * 8;
-    if (rs[RS_DONE]) return;
     const int M = pb.matchCount[pair];
-    const int it0 = chunk * kRansacChunk;
-    const int nIt = min(kRansacChunk, pg.maxIters - it0);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid / kGroupLanes, gl = tid & (kGroupLanes - 1);
+    const unsigned gmask = 0xFFFFu << (lane & 16);
+    const double T = (double)t32, tlo = T * (1.0 - 1e-6), thi = T * (1.0 + 1e-6);
     if (tid == 0) {
-        // cv::RNG stream, 5 distinct positions per iteration with single-index redraw (getSubset)
-        uint64_t state = ((uint64_t)(uint32_t)rs[RS_RNG_HI] << 32) | (uint32_t)rs[RS_RNG_LO];
-        for (int it = 0; it < nIt; ++it) {
-            int idx[5];
-            int i = 0;
-            while (i < 5) {
-                int v = (int)(cvrng_next(state) % (uint32_t)M);
-                bool dup = false;
-                for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
-                if (dup) continue;
-                idx[i++] = v;
-            }
-            for (int k = 0; k < 5; ++k) s_samples[it][k] = idx[k];
-        }
-        rs[RS_RNG_LO] = (int)(uint32_t)state;
-        rs[RS_RNG_HI] = (int)(uint32_t)(state >> 32);
+        sh.maxGood = 0;
+        sh.niters = pg.maxIters;
+        sh.done = rs[RS_DONE];
+        sh.it0 = 0;
+        sh.bestIter = -1; sh.bestModel = -1; sh.hasBest = 0;
+        sh.rng = ((unsigned long long)(uint32_t)rs[RS_RNG_HI] << 32) | (uint32_t)rs[RS_RNG_LO];
     }
     __syncthreads();
-    if (tid >= nIt) return;
     const double* np_ = pb.normPts + (size_t)pair * pg.maxkp * 4;
-    double x1[10], x2[10];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const double* p = np_ + (size_t)s_samples[tid][k] * 4;
-        x1[2 * k] = p[0]; x1[2 * k + 1] = p[1];
-        x2[2 * k] = p[2]; x2[2 * k + 1] = p[3];
-        pb.samples[((size_t)pair * pg.maxIters + it0 + tid) * 5 + k] = s_samples[tid][k];
-    }
-    double* models = pb.models + ((size_t)pair * kRansacChunk + tid) * kMaxModels * 9;
-    int n = five_point_solve(x1, x2, models);
-    pb.modelCount[(size_t)pair * kRansacChunk + tid] = n;
-}
-
-__global__ void __launch_bounds__(256) k_score(PairGeom pg, PairBuffers pb, int pair0, int chunk, float t32) {
-    const int pair = pair0 + blockIdx.y;
-    const int* rs = pb.ransacState + pair * 8;
-    if (rs[RS_DONE]) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 8 + warp;         // (iteration-in-chunk, model)
-    const int it = slot / kMaxModels, k = slot % kMaxModels;
-    if (it >= kRansacChunk) return;
-    const int itAbs = chunk * kRansacChunk + it;
-    if (itAbs >= rs[RS_NITERS] || itAbs >= pg.maxIters) return;
-    if (k >= pb.modelCount[(size_t)pair * kRansacChunk + it]) return;
-    const double* Eg = pb.models + (((size_t)pair * kRansacChunk + it) * kMaxModels + k) * 9;
-    double E[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) E[j] = Eg[j];
-    const int M = pb.matchCount[pair];
-    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
-    int good = 0;
-    for (int i = lane; i < M; i += 32) {
-        double4 p = np4[i];
-        float err = sampson_error_f32(E, p.x, p.y, p.z, p.w);
-        good += (err <= t32) ? 1 : 0;
-    }
-    good = __reduce_add_sync(0xffffffffu, good);
-    if (lane == 0) pb.modelGood[((size_t)pair * kRansacChunk + it) * kMaxModels + k] = good;
-}
-
-__global__ void k_replay(PairGeom pg, PairBuffers pb, int pair0, int nPairs, int chunk) {
-    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= nPairs) return;
-    const int pair = pair0 + pi;
-    int* rs = pb.ransacState + pair * 8;
-    if (rs[RS_DONE]) return;
-    const int M = pb.matchCount[pair];
-    int maxGood = rs[RS_MAXGOOD], niters = rs[RS_NITERS];
-    const int it0 = chunk * kRansacChunk;
-    const int itEnd = min(it0 + kRansacChunk, pg.maxIters);
-    int it = it0;
-    for (; it < itEnd; ++it) {
-        if (it >= niters) break;
-        const int nm = pb.modelCount[(size_t)pair * kRansacChunk + (it - it0)];
-        for (int k = 0; k < nm; ++k) {
-            int good = pb.modelGood[((size_t)pair * kRansacChunk + (it - it0)) * kMaxModels + k];
-            if (good > max(maxGood, 4)) {
-                maxGood = good;
-                const double* Eg = pb.models + (((size_t)pair * kRansacChunk + (it - it0)) * kMaxModels + k) * 9;
-                for (int j = 0; j < 9; ++j) pb.bestE[pair * 9 + j] = Eg[j];
-                rs[RS_BESTITER] = it;
-                rs[RS_BESTMODEL] = k;
-                rs[RS_HASBEST] = 1;
-                niters = ransac_update_num_iters(pg.prob, (double)(M - good) / M, 5, niters);
+    const double4* np4 = reinterpret_cast<const double4*>(np_);
+    while (!sh.done) {
+        const int it0 = sh.it0;
+        const int nIt = min(kRansacGroups, min(sh.niters, pg.maxIters) - it0);
+        __syncthreads();                     // everyone has read the loop state before thread 0 touches it again
+        if (tid == 0) {
+            uint64_t state = sh.rng;
+            for (int it = 0; it < nIt; ++it) {
+                int idx[5];
+                int i = 0;
+                while (i < 5) {
+                    const int v = (int)(cvrng_next(state) % (uint32_t)M);
+                    bool dup = false;
+                    for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
+                    if (dup) continue;
+                    idx[i++] = v;
+                }
+                for (int k = 0; k < 5; ++k) sh.samples[it][k] = idx[k];
             }
+            sh.rng = state;
         }
+        __syncthreads();
+        if (grp < nIt) {
+            double x1[10], x2[10];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double4 p = np4[sh.samples[grp][k]];
+                x1[2 * k] = p.x; x1[2 * k + 1] = p.y;
+                x2[2 * k] = p.z; x2[2 * k + 1] = p.w;
+            }
+            const int n = five_point_solve_group(x1, x2, sh.scratch[grp], &sh.models[grp][0][0], gmask);
+            if (gl == 0) sh.modelCount[grp] = n;
+            if (gl < 5) pb.samples[((size_t)pair * pg.maxIters + it0 + grp) * 5 + gl] = sh.samples[grp][gl];
+        }
+        __syncthreads();
+        for (int slot = warp; slot < nIt * kMaxModels; slot += kRansacThreads / 32) {
+            const int h = slot / kMaxModels, k = slot - h * kMaxModels;
+            if (k >= sh.modelCount[h]) continue;
+            double E[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) E[j] = sh.models[h][k][j];
+            int good = 0;
+            for (int i = lane; i < M; i += 32) {
+                const double4 p = np4[i];
+                good += sampson_inlier(E, p.x, p.y, p.z, p.w, t32, tlo, thi) ? 1 : 0;
+            }
+            good = __reduce_add_sync(0xffffffffu, good);
+            if (lane == 0) sh.modelGood[h][k] = good;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int maxGood = sh.maxGood, niters = sh.niters;
+            int it = it0;
+            for (; it < it0 + nIt; ++it) {
+                if (it >= niters) break;
+                const int h = it - it0, nm = sh.modelCount[h];
+                for (int k = 0; k < nm; ++k) {
+                    const int good = sh.modelGood[h][k];
+                    if (good > max(maxGood, 4)) {
+                        maxGood = good;
+                        for (int j = 0; j < 9; ++j) sh.bestE[j] = sh.models[h][k][j];
+                        sh.bestIter = it; sh.bestModel = k; sh.hasBest = 1;
+                        niters = ransac_update_num_iters(pg.prob, (double)(M - good) / M, 5, niters);
+                    }
+                }
+            }
+            sh.maxGood = maxGood;
+            sh.niters = niters;
+            sh.it0 = it;
+            if (it >= niters || it >= pg.maxIters) sh.done = 1;
+        }
+        __syncthreads();
     }
-    rs[RS_MAXGOOD] = maxGood;
-    rs[RS_NITERS] = niters;
-    if (it >= niters || it >= pg.maxIters) rs[RS_DONE] = 1;
-}
-
-// ================================================================================================ recoverPose
-__global__ void __launch_bounds__(256) k_pose_prep(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
-    __shared__ int s_cnt;
-    const int pi = blockIdx.x, pair = pair0 + pi;
-    const int* rs = pb.ransacState + pair * 8;
-    const int M = pb.matchCount[pair];
+    // ---- final state, mask of the winning model, SVD(E) -> R1, R2, t  (first half of recoverPose)
     PoseScratch& sc = ps[pair];
-    if (threadIdx.x == 0) { s_cnt = 0; for (int k = 0; k < 4; ++k) sc.good[k] = 0; }
-    __syncthreads();
     uint8_t* mask = pb.ransacMask + (size_t)pair * pg.maxkp;
-    if (!rs[RS_HASBEST]) {
-        for (int i = threadIdx.x; i < M; i += 256) mask[i] = 0;
-        if (threadIdx.x == 0) sc.nInl = 0;
+    const int hasBest = sh.hasBest;
+    if (tid == 0) {
+        rs[RS_MAXGOOD] = sh.maxGood; rs[RS_NITERS] = sh.niters; rs[RS_DONE] = 1;
+        rs[RS_BESTITER] = sh.bestIter; rs[RS_BESTMODEL] = sh.bestModel; rs[RS_HASBEST] = hasBest;
+        rs[RS_RNG_LO] = (int)(uint32_t)sh.rng; rs[RS_RNG_HI] = (int)(uint32_t)(sh.rng >> 32);
+        sh.cnt = 0;
+        for (int k = 0; k < 4; ++k) sc.good[k] = 0;
+    }
+    __syncthreads();
+    if (!hasBest) {
+        for (int i = tid; i < M; i += kRansacThreads) mask[i] = 0;
+        if (tid == 0) sc.nInl = 0;
         return;
     }
     double E[9];
-    for (int j = 0; j < 9; ++j) E[j] = pb.bestE[pair * 9 + j];
-    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) E[j] = sh.bestE[j];
+    if (tid < 9) pb.bestE[pair * 9 + tid] = E[tid];
     int local = 0;
-    for (int i = threadIdx.x; i < M; i += 256) {
-        double4 p = np4[i];
-        int in = sampson_error_f32(E, p.x, p.y, p.z, p.w) <= t32 ? 1 : 0;
+    for (int i = tid; i < M; i += kRansacThreads) {
+        const double4 p = np4[i];
+        const int in = sampson_inlier(E, p.x, p.y, p.z, p.w, t32, tlo, thi) ? 1 : 0;
         mask[i] = (uint8_t)in;
         local += in;
     }
     local = __reduce_add_sync(0xffffffffu, local);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+    if (lane == 0) atomicAdd(&sh.cnt, local);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sc.nInl = s_cnt;
+    if (tid == 0) {
+        sc.nInl = sh.cnt;
         decompose_essential(E, sc.R1, sc.R2, sc.t);
     }
 }
 
+// ================================================================================================ recoverPose
 __global__ void __launch_bounds__(128) k_cheirality(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0) {
     const int pi = blockIdx.y, pair = pair0 + pi;
     const int* rs = pb.ransacState + pair * 8;
@@ -393,17 +425,8 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
     const double thr = pg.threshold / ((fx + fy) / 2.0);
     const float t32 = (float)(thr * thr);
     PoseScratch* ps = pb.poseScratch;
-    for (int c = 0; c < pg.nChunks; ++c) {
-        { ProfScope ps_(PF_SOLVE, st); k_solve<<<nPairs, kRansacChunk, 0, st>>>(pg, pb, pair0, c); }
-        debug_sync("k_solve", st);
-        { ProfScope ps_(PF_SCORE, st); k_score<<<dim3(kRansacChunk * kMaxModels / 8, nPairs), 256, 0, st>>>(pg, pb, pair0, c, t32); }
-        debug_sync("k_score", st);
-        { ProfScope ps_(PF_REPLAY, st); k_replay<<<(nPairs + 63) / 64, 64, 0, st>>>(pg, pb, pair0, nPairs, c); }
-        g_pair_launches += 3;
-        debug_sync("k_replay", st);
-    }
-    { ProfScope ps_(PF_POSE_PREP, st); k_pose_prep<<<nPairs, 256, 0, st>>>(pg, pb, ps, pair0, t32); }
-    debug_sync("k_pose_prep", st);
+    { ProfScope ps_(PF_RANSAC, st); k_ransac<<<nPairs, kRansacThreads, 0, st>>>(pg, pb, ps, pair0, t32); }
+    debug_sync("k_ransac", st);
     { ProfScope ps_(PF_CHEIRALITY, st); k_cheirality<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(pg, pb, ps, pair0); }
     debug_sync("k_cheirality", st);
     { ProfScope ps_(PF_POSE_FINAL, st); k_pose_final<<<nPairs, 256, 0, st>>>(og, ob, pg, pb, ps, slotA0, pair0); }
@@ -415,7 +438,11 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
                   int nPairs, const double* K, cudaStream_t st) {
     if (nPairs <= 0) return;
     const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-    { ProfScope ps_(PF_NN, st); k_nn<<<dim3((pg.maxkp + 127) / 128, 2, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0); }
+    {
+        ProfScope ps_(PF_NN, st);
+        cudaMemsetAsync(pb.nnIdx + (size_t)pair0 * 2 * pg.maxkp, 0xFF, sizeof(int) * 2 * (size_t)nPairs * pg.maxkp, st);
+        k_nn<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+    }
     { ProfScope ps_(PF_SORT, st); k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy); }
     g_pair_launches += 2;
     debug_sync("k_nn+sort", st);

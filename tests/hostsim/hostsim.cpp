@@ -135,6 +135,10 @@ void hs_triangulate(const double* R, const double* t, double x1, double y1, doub
     triangulate_one(R, t, x1, y1, x2, y2, X);
 }
 float hs_sampson(const double* E, double x1, double y1, double x2, double y2) { return sampson_error_f32(E, x1, y1, x2, y2); }
+int hs_sampson_inlier(const double* E, double x1, double y1, double x2, double y2, float t32) {
+    double T = (double)t32;
+    return sampson_inlier(E, x1, y1, x2, y2, t32, T * (1.0 - 1e-6), T * (1.0 + 1e-6)) ? 1 : 0;
+}
 int hs_update_iters(double p, double ep, int mp, int mx) { return ransac_update_num_iters(p, ep, mp, mx); }
 void hs_rng_stream(uint32_t* out, int n) {
     uint64_t s = 0xFFFFFFFFFFFFFFFFull;

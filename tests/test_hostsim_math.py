@@ -157,3 +157,22 @@ def test_pose_decomposition_and_cheirality(hostsim, golden):
     err = P.sampson_errors(E, x1, x2)
     mine = np.array([hostsim.hs_sampson(ptr(E), float(a[0]), float(a[1]), float(b[0]), float(b[1])) for a, b in zip(x1, x2)], np.float32)
     assert np.mean(mine == err) > 0.98 and np.allclose(mine, err, rtol=1e-6)   # numpy matmul sums in another order: 1-ulp float32 differences
+
+
+def test_sampson_inlier_shortcut_equals_exact_decision(hostsim, golden):
+    """the division-free fast path of sampson_inlier decides exactly like (float)(num/den) <= t32, also at the boundary"""
+    hostsim.hs_sampson_inlier.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_float]
+    E = np.ascontiguousarray(golden["c5_E"])
+    x1 = P.normalize_points(golden["c5_p1"], golden["c5_K"]); x2 = P.normalize_points(golden["c5_p2"], golden["c5_K"])
+    errs = np.array([hostsim.hs_sampson(ptr(E), float(a[0]), float(a[1]), float(b[0]), float(b[1])) for a, b in zip(x1, x2)], np.float32)
+    # thresholds: the usual one, plus each sample's own error and its float neighbours (boundary cases)
+    K = golden["c5_K"]
+    t_usual = np.float32((1.0 / ((K[0, 0] + K[1, 1]) / 2)) ** 2)
+    idx = np.random.default_rng(0).choice(len(x1), 300, replace=False)
+    for i in idx:
+        a, b = x1[i], x2[i]
+        for t in (t_usual, errs[i], np.nextafter(errs[i], np.float32(0)), np.nextafter(errs[i], np.float32(1))):
+            if not t > 0:
+                continue
+            got = hostsim.hs_sampson_inlier(ptr(E), float(a[0]), float(a[1]), float(b[0]), float(b[1]), float(t))
+            assert got == int(errs[i] <= t)
