@@ -35,6 +35,7 @@ struct dvo_ctx {
     uint8_t* h_frameStage = nullptr;
     long long launchBase = 0;
     int carrySlot = -1;                // slot holding the last frame of the previous dvo_sequence_step
+    SideStreams ss;
 };
 
 #define CK(call)                                                                                     \
@@ -287,6 +288,16 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
         rc = build_tensor_maps(ctx);
         if (rc != 0) return rc;
     }
+    if (getenv("DVO_NO_SIDE_STREAMS") == nullptr) {
+        CK(cudaStreamCreateWithFlags(&ctx->ss.side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->ss.copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ss.evFork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ss.evJoin, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->ss.evCopied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ss.evStageFree[i], cudaEventDisableTiming));
+        }
+    }
     orb_kernels_init();
     pair_kernels_init((int)(pg.sortCap * sizeof(uint32_t)));
     CK(cudaDeviceSynchronize());
@@ -299,6 +310,15 @@ void dvo_destroy(dvo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ss.stage[i]) cudaFree(ctx->ss.stage[i]);
+        if (ctx->ss.evCopied[i]) cudaEventDestroy(ctx->ss.evCopied[i]);
+        if (ctx->ss.evStageFree[i]) cudaEventDestroy(ctx->ss.evStageFree[i]);
+    }
+    if (ctx->ss.evFork) cudaEventDestroy(ctx->ss.evFork);
+    if (ctx->ss.evJoin) cudaEventDestroy(ctx->ss.evJoin);
+    if (ctx->ss.side) cudaStreamDestroy(ctx->ss.side);
+    if (ctx->ss.copy) cudaStreamDestroy(ctx->ss.copy);
     if (ctx->h_poseStage) cudaFreeHost(ctx->h_poseStage);
     if (ctx->h_frameStage) cudaFreeHost(ctx->h_frameStage);
     delete ctx;
@@ -327,11 +347,40 @@ int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, si
     }
     cudaStream_t st = (cudaStream_t)stream;
     const LevelGeom& l0 = ctx->og.lv[0];
-    cudaMemcpyKind k = kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    for (int i = 0; i < n; ++i) {
-        CK(cudaMemcpy2DAsync(ctx->ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
-                             frames + (size_t)i * frame_stride, pitch, l0.w, l0.h, k, st));
+    if (n == 0) return DVO_OK;
+    if (kind == 0) {
+        launch_load_frames(ctx->og, ctx->ob, frames, n, pitch, frame_stride, slot0, st);
+        CK(cudaGetLastError());
+        return DVO_OK;
     }
+    SideStreams& ss = ctx->ss;
+    if (ss.copy == nullptr) {   // side streams disabled: plain in-order copies
+        for (int i = 0; i < n; ++i) {
+            CK(cudaMemcpy2DAsync(ctx->ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
+                                 frames + (size_t)i * frame_stride, pitch, l0.w, l0.h, cudaMemcpyHostToDevice, st));
+        }
+        return DVO_OK;
+    }
+    // Host frames: H2D on the copy stream into one of two staging buffers (so the upload of the next batch overlaps the
+    // kernels of this one), then one kernel on the compute stream moves them into the slots.
+    const size_t frameBytes = (size_t)l0.w * l0.h;
+    const int bsel = ss.stageIdx;
+    ss.stageIdx ^= 1;
+    if (ss.stage[bsel] == nullptr) CK(cudaMalloc(&ss.stage[bsel], frameBytes * ctx->nSlots));
+    if (ss.stageUsed[bsel]) CK(cudaStreamWaitEvent(ss.copy, ss.evStageFree[bsel], 0));
+    if (pitch == (size_t)l0.w && frame_stride == frameBytes) {
+        CK(cudaMemcpyAsync(ss.stage[bsel], frames, frameBytes * n, cudaMemcpyHostToDevice, ss.copy));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CK(cudaMemcpy2DAsync(ss.stage[bsel] + (size_t)i * frameBytes, l0.w, frames + (size_t)i * frame_stride, pitch, l0.w, l0.h,
+                                 cudaMemcpyHostToDevice, ss.copy));
+    }
+    CK(cudaEventRecord(ss.evCopied[bsel], ss.copy));
+    CK(cudaStreamWaitEvent(st, ss.evCopied[bsel], 0));
+    launch_load_frames(ctx->og, ctx->ob, ss.stage[bsel], n, l0.w, frameBytes, slot0, st);
+    CK(cudaEventRecord(ss.evStageFree[bsel], st));
+    ss.stageUsed[bsel] = true;
+    CK(cudaGetLastError());
     return DVO_OK;
 }
 
@@ -340,7 +389,7 @@ int dvo_orb(dvo_ctx* ctx, int slot0, int n, void* stream) {
         if (ctx) ctx->err = "dvo_orb: slot range out of bounds";
         return DVO_E_INVALID;
     }
-    launch_orb(ctx->og, ctx->ob, &ctx->tmaps, ctx->useTma, slot0, n, (cudaStream_t)stream);
+    launch_orb(ctx->og, ctx->ob, &ctx->tmaps, ctx->useTma, slot0, n, (cudaStream_t)stream, &ctx->ss);
     CK(cudaGetLastError());
     return DVO_OK;
 }

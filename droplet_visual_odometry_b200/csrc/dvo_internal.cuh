@@ -122,9 +122,22 @@ struct ProfScope {
     ~ProfScope() { prof_end(id, st); }
 };
 
+// Side stream + events of a context: k_blur depends only on the pyramid, so it runs beside the latency-bound
+// compact -> select -> angle chain; host frames are staged through a double buffer on a copy stream.
+struct SideStreams {
+    cudaStream_t side = nullptr, copy = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evStageFree[2] = {nullptr, nullptr};
+    bool stageUsed[2] = {false, false};
+    uint8_t* stage[2] = {nullptr, nullptr};
+    int stageIdx = 0;
+};
+
 // ---- launchers (orb_kernels.cu / pair_kernels.cu) ---------------------------------------------------------------
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
-                cudaStream_t st);
+                cudaStream_t st, const SideStreams* ss);
+void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_src, int n, size_t pitch, size_t frameStride,
+                        int slot0, cudaStream_t st);
 void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
                   int pair0, int nPairs, const double* K, cudaStream_t st);
 

@@ -21,6 +21,7 @@ struct SolveScratch {        // per group, shared memory
     double EE[36];           // null-space basis, EE[b*9 + k]
     double eet[6][10];       // E E^T entries (00,01,02,11,12,22) as quadratic polynomials
     double red[10][10];      // right half of the reduced 10x20 system, indexed by pivot column
+    double zr[10], zi[10];   // Aberth iterates, exchanged through shared memory
 };
 
 __device__ __forceinline__ double gshfl(unsigned gmask, double v, int src) { return __shfl_sync(gmask, v, src, kGroupLanes); }
@@ -29,6 +30,11 @@ __device__ __forceinline__ double gsum(unsigned gmask, double v) {
 #pragma unroll
     for (int m = 8; m > 0; m >>= 1) v += gshfl_xor(gmask, v, m);
     return v;
+}
+
+__device__ __forceinline__ cplx crcp(cplx a) {     // 1/a with one reciprocal
+    const double inv = 1.0 / (a.re * a.re + a.im * a.im);
+    return cplx{a.re * inv, -a.im * inv};
 }
 
 __device__ __forceinline__ int sym6(int i, int j) {   // index of eet[min][max]
@@ -233,36 +239,46 @@ __device__ int five_point_solve_group(const double* x1, const double* x2, SolveS
         const double ang = 2.0 * 3.14159265358979323846 * (gl < 10 ? gl : 0) / 10 + 0.4;
         z = cplx{r * cos(ang), r * sin(ang)};
     }
+    // A root is frozen once its step is below 1e-13 relative or |p(z)| is within the rounding noise of Horner's rule
+    // (|p| <= 64 eps * sum |c_k||z|^k); the loop ends when all ten are frozen.  F re-polishes the real ones.
+    bool frozen = gl >= 10;
     for (int it = 0; it < 40; ++it) {
+        if (gl < 10) { S.zr[gl] = z.re; S.zi[gl] = z.im; }
+        __syncwarp(gmask);
         cplx p{c[0], 0}, dp{0, 0};
+        const double az = sqrt(z.re * z.re + z.im * z.im);
+        double pb = fabs(c[0]);
 #pragma unroll
         for (int k = 1; k <= 10; ++k) {
             dp = cadd(cmul(dp, z), p);
             p = cadd(cmul(p, z), cplx{c[k], 0});
+            pb = pb * az + fabs(c[k]);
         }
+        if (fabs(p.re) + fabs(p.im) <= 64.0 * DBL_EPSILON * pb) frozen = true;
         if (dp.re * dp.re + dp.im * dp.im == 0) dp = cplx{1e-300, 0};
-        const cplx w = cmul(p, cinv(dp));
+        const cplx w = cmul(p, crcp(dp));
         cplx s{0, 0};
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
-            cplx zj{gshfl(gmask, z.re, j), gshfl(gmask, z.im, j)};
+            const cplx zj{S.zr[j], S.zi[j]};
             if (j != gl) {
                 cplx d = csub(z, zj);
                 if (d.re == 0 && d.im == 0) d = cplx{1e-300, 0};
-                s = cadd(s, cinv(d));
+                s = cadd(s, crcp(d));
             }
         }
         cplx den = csub(cplx{1, 0}, cmul(w, s));
         if (den.re == 0 && den.im == 0) den = cplx{1e-300, 0};
-        const cplx step = cmul(w, cinv(den));
-        z = csub(z, step);
-        const double sm = fabs(step.re) + fabs(step.im);
-        const double zm = fabs(z.re) + fabs(z.im);
-        double rel = (gl < 10) ? sm / (zm > 1e-30 ? zm : 1e-30) : 0.0;
-        if (!(rel == rel)) rel = 1e300;     // NaN never counts as converged
-#pragma unroll
-        for (int m = 8; m > 0; m >>= 1) rel = fmax(rel, gshfl_xor(gmask, rel, m));
-        if (rel < 1e-14) break;             // uniform in the group
+        const cplx step = cmul(w, crcp(den));
+        if (!frozen) {
+            z = csub(z, step);
+            const double sm = fabs(step.re) + fabs(step.im);
+            const double zm = fabs(z.re) + fabs(z.im);
+            if (sm <= 1e-13 * (zm > 1e-30 ? zm : 1e-30)) frozen = true;     // false for NaN
+        }
+        const unsigned live = __ballot_sync(gmask, !frozen) & gmask;
+        __syncwarp(gmask);                  // all reads of S.z* done before the next iteration overwrites them
+        if (live == 0) break;               // uniform in the group
     }
 
     // ---- F: real roots -> models
@@ -319,8 +335,6 @@ __device__ int five_point_solve_group(const double* x1, const double* x2, SolveS
     // The scalar code sorts ALL real roots by z (stable) and then drops the degenerate ones, so among the surviving
     // models the order is (z, root index) ascending.
     int rank = 0, count = 0;
-    const bool realroot = gl < 10 && (fabs(z.im) <= 1e-10);
-    (void)realroot;
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
         const double zj = gshfl(gmask, zr, j);

@@ -17,6 +17,8 @@
 
 namespace dvo {
 
+static long long g_launches = 0;
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
@@ -764,7 +766,6 @@ __global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot
 }
 
 // =========================================================================================== launcher
-static long long g_launches = 0;
 long long orb_launch_count() { return g_launches; }
 
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -812,8 +813,33 @@ void debug_sync(const char* name, cudaStream_t st) {
     fprintf(stderr, "[dvo] %-16s %s\n", name, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
 }
 
+// Frames (device memory, arbitrary pitch) -> level 0 of the slots, one launch for the whole batch.
+__global__ void __launch_bounds__(256) k_load_frames(OrbGeom g, OrbBuffers b, const uint8_t* __restrict__ src, size_t pitch,
+                                                     size_t frameStride, int slot0, int vec16) {
+    const LevelGeom& l0 = g.lv[0];
+    const int y = blockIdx.y, f = blockIdx.z;
+    const uint8_t* s = src + (size_t)f * frameStride + (size_t)y * pitch;
+    uint8_t* d = b.pyr + (size_t)(slot0 + f) * g.slotStride + l0.off + (size_t)y * l0.pitch;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * 16;
+    if (x >= l0.w) return;
+    if (vec16 && x + 16 <= l0.w) {
+        *reinterpret_cast<uint4*>(d + x) = __ldg(reinterpret_cast<const uint4*>(s + x));
+    } else {
+        for (int k = 0; k < 16 && x + k < l0.w; ++k) d[x + k] = s[x + k];
+    }
+}
+
+void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_src, int n, size_t pitch, size_t frameStride,
+                        int slot0, cudaStream_t st) {
+    if (n <= 0) return;
+    const int vec16 = ((reinterpret_cast<uintptr_t>(d_src) | pitch | frameStride) & 15) == 0 ? 1 : 0;
+    dim3 grid((g.lv[0].w + 4095) / 4096, g.lv[0].h, n);
+    k_load_frames<<<grid, 256, 0, st>>>(g, b, d_src, pitch, frameStride, slot0, vec16);
+    ++g_launches;
+}
+
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
-                cudaStream_t st) {
+                cudaStream_t st, const SideStreams* ss) {
     if (nSlots <= 0) return;
     cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
     for (int L = 1; L < g.nlevels; ++L) {
@@ -831,6 +857,14 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
         ++g_launches;
         debug_sync("k_fast_nms", st);
     }
+    const bool fork = ss != nullptr && ss->side != nullptr;
+    if (fork) {      // k_blur beside compact -> select -> angle
+        cudaEventRecord(ss->evFork, st);
+        cudaStreamWaitEvent(ss->side, ss->evFork, 0);
+        { ProfScope ps_(PF_BLUR, ss->side); k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, ss->side>>>(g, b, slot0); }
+        ++g_launches;
+        cudaEventRecord(ss->evJoin, ss->side);
+    }
     { ProfScope ps_(PF_COMPACT, st); k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_compact", st);
@@ -840,8 +874,12 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     { ProfScope ps_(PF_ANGLE, st); k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_angle_pack", st);
-    { ProfScope ps_(PF_BLUR, st); k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
-    ++g_launches;
+    if (fork) {
+        cudaStreamWaitEvent(st, ss->evJoin, 0);
+    } else {
+        { ProfScope ps_(PF_BLUR, st); k_blur<<<dim3(g.tilesPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
+        ++g_launches;
+    }
     debug_sync("k_blur", st);
     { ProfScope ps_(PF_BRIEF, st); k_brief<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;

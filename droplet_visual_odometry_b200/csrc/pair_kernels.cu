@@ -233,19 +233,27 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuff
             if (gl < 5) pb.samples[((size_t)pair * pg.maxIters + it0 + grp) * 5 + gl] = sh.samples[grp][gl];
         }
         __syncthreads();
-        for (int slot = warp; slot < nIt * kMaxModels; slot += kRansacThreads / 32) {
-            const int h = slot / kMaxModels, k = slot - h * kMaxModels;
-            if (k >= sh.modelCount[h]) continue;
-            double E[9];
+        // Scoring: matches live in registers (two per thread per sweep), the models are broadcast from shared memory,
+        // so each correspondence is read once per chunk and the loop is bound by the FP64 pipe, not by load latency.
+        for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads) (&sh.modelGood[0][0])[i] = 0;
+        __syncthreads();
+        for (int base = 0; base < M; base += 2 * kRansacThreads) {
+            const int i0 = base + tid, i1 = base + kRansacThreads + tid;
+            const bool v0 = i0 < M, v1 = i1 < M;
+            const double4 p0 = v0 ? np4[i0] : make_double4(0, 0, 0, 0);
+            const double4 p1 = v1 ? np4[i1] : make_double4(0, 0, 0, 0);
+            for (int h = 0; h < nIt; ++h) {
+                const int nm = sh.modelCount[h];
+                for (int k = 0; k < nm; ++k) {
+                    double E[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) E[j] = sh.models[h][k][j];
-            int good = 0;
-            for (int i = lane; i < M; i += 32) {
-                const double4 p = np4[i];
-                good += sampson_inlier(E, p.x, p.y, p.z, p.w, t32, tlo, thi) ? 1 : 0;
+                    for (int j = 0; j < 9; ++j) E[j] = sh.models[h][k][j];
+                    int good = (v0 && sampson_inlier(E, p0.x, p0.y, p0.z, p0.w, t32, tlo, thi)) ? 1 : 0;
+                    good += (v1 && sampson_inlier(E, p1.x, p1.y, p1.z, p1.w, t32, tlo, thi)) ? 1 : 0;
+                    good = __reduce_add_sync(0xffffffffu, good);
+                    if (lane == 0 && good) atomicAdd(&sh.modelGood[h][k], good);
+                }
             }
-            good = __reduce_add_sync(0xffffffffu, good);
-            if (lane == 0) sh.modelGood[h][k] = good;
         }
         __syncthreads();
         if (tid == 0) {
