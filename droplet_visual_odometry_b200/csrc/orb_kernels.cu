@@ -70,8 +70,10 @@ template <bool kUseTma>
 __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
     __shared__ __align__(128) uint8_t raw[kFastBoxH * kFastBoxW];
     __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
-    __shared__ uint16_t list1[(kTileH + 2) * (kTileW + 2)], list2[(kTileH + 2) * (kTileW + 2)];
+    __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
+    __shared__ uint16_t list2[(kTileH + 2) * (kTileW + 2)];
     __shared__ int s_n1, s_n2;
+    __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
     const int tile = blockIdx.x;
@@ -138,46 +140,51 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
 
     // ---- phase 1: packed prefilter, 4 adjacent positions per thread (quads aligned to 4 raw columns).
     // Ring positions are 130 x 34 (tile + 1): raw rows 3..36, raw cols 15..144; a position is coded by its raw offset.
+    // Thread layout: 34 quad columns x 7 rows per sweep (238 of 256 threads), 5 sweeps cover the 34 ring rows.
     const int th = g.fastThreshold;
     constexpr int kRowWords = kFastBoxW / 4;
-    constexpr int kQuadsX = 34, kQuadsY = kTileH + 2;
-    for (int q0 = 0; q0 < kQuadsX * kQuadsY; q0 += 256) {
-        const int q = q0 + tid;
-        uint32_t pass = 0;
-        int code0 = 0;
-        if (q < kQuadsX * kQuadsY) {
-            const int qy = q / kQuadsX, qx = q - qy * kQuadsX;
-            code0 = (qy + 3) * kFastBoxW + 12 + 4 * qx;
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + code0);
-            const uint32_t c = rp[0], lw = rp[-1], rw = rp[1];
-            const uint32_t up = rp[-3 * kRowWords], dn = rp[3 * kRowWords];
-            const uint32_t e = __byte_perm(c, rw, 0x6543), w = __byte_perm(lw, c, 0x4321);
-            pass = fast_prefilter_u8x4(c, up, e, dn, w, th);
-            // positions outside the ring columns or outside the level's FAST domain
-            const int sy = y0 - 4 + qy + 3;
-            if (sy < 3 || sy >= lv.h - 3) pass = 0;
-            const int sx0 = x0 - kFastHaloL + 12 + 4 * qx;
+    constexpr int kQuadsX = 34, kQuadsY = kTileH + 2, kRowsPerSweep = 7;
+    {
+        const int qx = tid % kQuadsX, qrow = tid / kQuadsX;          // qrow == 7 for the 18 spare threads
+        // byte k of this thread's quads is a ring column inside the level's FAST domain?
+        uint32_t colmask = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int rc = 12 + 4 * qx + k, sx = sx0 + k;
-                if (rc < 15 || rc > 144 || sx < 3 || sx >= lv.w - 3) pass &= ~(0x80u << (8 * k));
+        for (int k = 0; k < 4; ++k) {
+            const int rc = 12 + 4 * qx + k, sx = x0 - kFastHaloL + rc;
+            if (rc >= 15 && rc <= 144 && sx >= 3 && sx < lv.w - 3) colmask |= 0x80u << (8 * k);
+        }
+        if (qrow >= kRowsPerSweep) colmask = 0;
+        for (int qy0 = 0; qy0 < kQuadsY; qy0 += kRowsPerSweep) {
+            const int qy = qy0 + qrow;
+            const int sy = y0 - 1 + qy;
+            uint32_t pass = 0;
+            const int code0 = (qy + 3) * kFastBoxW + 12 + 4 * qx;
+            if (colmask != 0 && qy < kQuadsY && sy >= 3 && sy < lv.h - 3) {
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + code0);
+                const uint32_t c = rp[0], lw = rp[-1], rw = rp[1];
+                const uint32_t up = rp[-3 * kRowWords], dn = rp[3 * kRowWords];
+                const uint32_t e = __byte_perm(c, rw, 0x6543), w = __byte_perm(lw, c, 0x4321);
+                pass = fast_prefilter_u8x4(c, up, e, dn, w, th) & colmask;
+            }
+            // warp-aggregated append (exclusive scan of the per-thread counts)
+            const int cnt = __popc(pass);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            int base = 0;
+            if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (pass) {
+                int pos = base + incl - cnt;
+                if (pass & 0x00000080u) list1[pos++] = (uint16_t)(code0);
+                if (pass & 0x00008000u) list1[pos++] = (uint16_t)(code0 + 1);
+                if (pass & 0x00800000u) list1[pos++] = (uint16_t)(code0 + 2);
+                if (pass & 0x80000000u) list1[pos] = (uint16_t)(code0 + 3);
             }
         }
-        // warp-aggregated append
-        const int cnt = __popc(pass);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        int base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + incl - cnt;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (pass & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(code0 + k);
     }
     __syncthreads();
 
@@ -204,7 +211,10 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     }
     __syncthreads();
 
-    // ---- phase 3: scores of the corners
+    // ---- phase 3: scores of the corners into the ring score tile; list1 is dead now and becomes the output tile
+    uint8_t* outmap = reinterpret_cast<uint8_t*>(list1);        // [kTileH][kTileW], zero = no keypoint
+    reinterpret_cast<uint4*>(outmap)[tid] = make_uint4(0, 0, 0, 0);
+    if (tid < kTileH) s_rowcnt[tid] = 0;
     const int n2 = s_n2;
     for (int i = tid; i < n2; i += 256) {
         const int code = list2[i];
@@ -217,37 +227,36 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     }
     __syncthreads();
 
-    // NMS + write map + per-row survivor counts
-    uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
-    int* rowCount = b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase;
-    const int warp = tid >> 5;
+    // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull
     const int border = 31;
-    for (int r = warp; r < kTileH; r += 8) {
-        int y = y0 + r;
-        if (y >= lv.h) break;
-        uint32_t word = 0;
-        int cnt = 0;
-        bool rowIn = (y >= border && y < lv.h - border);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int cx = lane * 4 + k + 1, cy = r + 1;
-            int x = x0 + lane * 4 + k;
-            int s = sc[cy * 136 + cx];
-            bool keep = rowIn && s > 0 && x >= border && x < lv.w - border;
-            if (keep) {
-                const uint8_t* q = sc + cy * 136 + cx;
-                keep = s > q[-1] && s > q[1] && s > q[-136 - 1] && s > q[-136] && s > q[-136 + 1] && s > q[136 - 1] &&
-                       s > q[136] && s > q[136 + 1];
-            }
-            if (keep) {
-                word |= (uint32_t)s << (8 * k);
-                ++cnt;
-            }
+    for (int i = tid; i < n2; i += 256) {
+        const int code = list2[i];
+        const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
+        const int cy = ry - 3, cx = rx - 15;                   // ring coordinates: tile pixel (cx-1, cy-1)
+        const int x = x0 + cx - 1, y = y0 + cy - 1;
+        if (cx < 1 || cx > kTileW || cy < 1 || cy > kTileH) continue;
+        if (x < border || x >= lv.w - border || y < border || y >= lv.h - border) continue;
+        const uint8_t* q = sc + cy * 136 + cx;
+        const int sv = *q;
+        const bool keep = sv > q[-1] && sv > q[1] && sv > q[-136 - 1] && sv > q[-136] && sv > q[-136 + 1] && sv > q[136 - 1] &&
+                          sv > q[136] && sv > q[136 + 1];
+        if (keep) {
+            outmap[(cy - 1) * kTileW + (cx - 1)] = (uint8_t)sv;
+            atomicAdd(&s_rowcnt[cy - 1], 1);
         }
-        int xw = x0 + lane * 4;
-        if (xw < lv.pitch) *reinterpret_cast<uint32_t*>(map + (size_t)y * lv.pitch + xw) = word;
-        int total = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && total > 0) atomicAdd(rowCount + y, total);
+    }
+    __syncthreads();
+
+    // ---- phase 5: score map tile -> HBM (one 16-byte store per thread), per-row survivor counts
+    {
+        uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
+        const int r = tid >> 3, c16 = (tid & 7) * 16;
+        const int y = y0 + r;
+        if (y < lv.h) *reinterpret_cast<uint4*>(map + (size_t)y * lv.pitch + x0 + c16) = reinterpret_cast<const uint4*>(outmap)[tid];
+        if (tid < kTileH && y0 + tid < lv.h) {
+            const int c = s_rowcnt[tid];
+            if (c > 0) atomicAdd(b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase + y0 + tid, c);
+        }
     }
 }
 
@@ -297,11 +306,18 @@ __global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int sl
         int n = s_rowOff[rr + 1] - s_rowOff[rr];
         if (n == 0) continue;
         int running = s_rowOff[rr];
-        for (int xc = 0; xc < lv.w; xc += 128) {
-            int x = xc + lane * 4;
-            uint32_t word = 0;
-            if (x < lv.pitch) word = *reinterpret_cast<const uint32_t*>(map + (size_t)y * lv.pitch + x);
-            int c = ((word & 0xFFu) != 0) + ((word & 0xFF00u) != 0) + ((word & 0xFF0000u) != 0) + ((word & 0xFF000000u) != 0);
+        for (int xc = 0; xc < lv.w; xc += 512) {      // 16 pixels per lane per step
+            const int x = xc + lane * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (x < lv.pitch) v = *reinterpret_cast<const uint4*>(map + (size_t)y * lv.pitch + x);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // bytes != 0 -> one bit each
+                const uint32_t nz = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
+                c += __popc(nz);
+            }
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -309,12 +325,18 @@ __global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int sl
                 if (lane >= o) incl += nn;
             }
             int pos = running + incl - c;
+            if (c) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t s = (word >> (8 * k)) & 0xFFu;
-                if (s) {
-                    if (pos < lv.candCap) cand[pos] = (s << 24) | ((uint32_t)y << 12) | (uint32_t)(x + k);
-                    ++pos;
+                for (int q = 0; q < 4; ++q) {
+                    if (wv[q] == 0) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t sv = (wv[q] >> (8 * k)) & 0xFFu;
+                        if (sv) {
+                            if (pos < lv.candCap) cand[pos] = (sv << 24) | ((uint32_t)y << 12) | (uint32_t)(x + 4 * q + k);
+                            ++pos;
+                        }
+                    }
                 }
             }
             running += __shfl_sync(0xffffffffu, incl, 31);

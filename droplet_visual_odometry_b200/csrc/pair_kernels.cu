@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuff
     const int pair = pair0 + blockIdx.x;
     int* rs = pb.ransacState + pair * 8;
     const int M = pb.matchCount[pair];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int grp = tid / kGroupLanes, gl = tid & (kGroupLanes - 1);
     const unsigned gmask = 0xFFFFu << (lane & 16);
     const double T = (double)t32, tlo = T * (1.0 - 1e-6), thi = T * (1.0 + 1e-6);
