@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=50, help="new frames (= pairs) per step")
+    ap.add_argument("--batch", type=int, default=148, help="new frames (= pairs) per step (default: one k_ransac CTA per SM)")
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--nfeatures", type=int, default=2000)
@@ -335,8 +335,13 @@ def run_b200(a):
                         "k_cheirality": nkp * 33}.get(dom, nkp * 32)
             alg = per_pair * B
             achieved = alg * dcnt / (dms * 1e-3) / 1e9
+        # DRAM traffic per frame of the streaming kernels from the committed `ncu --set full` capture (profiles/, 1280x1024,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch / frames per launch); null for other sizes / kernels
+        ncu_traffic_per_frame = {"k_fast_nms": (213.71e6 + 176.72e6) / 50, "k_blur": (217.39e6 + 172.41e6) / 50} \
+            if (a.width, a.height) == (1280, 1024) else {}
+        traffic = int(ncu_traffic_per_frame[dom] * B) if dom in ncu_traffic_per_frame else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 6), "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": round(dms / tot_ms, 4), "algorithmic_bytes_per_launch": int(alg),
                     "avg_launch_ms": round(dms / max(dcnt, 1), 4)}
 

@@ -91,12 +91,19 @@ DVO_HD int imax(int a, int b) { return a > b ? a : b; }
 
 // Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
 DVO_HD bool fast_is_corner16(int v, const int* p, int t) {
-    uint32_t brighter = 0, darker = 0;   // d > t  /  d < -t  with d_k = v - p_k
+    // bit per ring pixel, shifted in at the bottom (ring order reversed -- contiguity is what matters):
+    // sign(p - lo) <=> p < v - t <=> d > t ;  sign(hi - p) <=> p > v + t <=> d < -t
+    uint32_t brighter = 0, darker = 0;
     const int lo = v - t, hi = v + t;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        brighter |= (uint32_t)(p[k] < lo) << k;
-        darker |= (uint32_t)(p[k] > hi) << k;
+#if defined(__CUDA_ARCH__)
+        brighter = __funnelshift_l((uint32_t)(p[k] - lo), brighter, 1);
+        darker = __funnelshift_l((uint32_t)(hi - p[k]), darker, 1);
+#else
+        brighter = (brighter << 1) | ((uint32_t)(p[k] - lo) >> 31);
+        darker = (darker << 1) | ((uint32_t)(hi - p[k]) >> 31);
+#endif
     }
     return ring_has9(brighter) || ring_has9(darker);
 }

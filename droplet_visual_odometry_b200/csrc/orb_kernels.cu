@@ -30,37 +30,48 @@ __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
 }
 
 // =========================================================================================== A.1 pyramid
+// Each thread owns 4 adjacent output columns (x coefficients and source offsets held in registers) and walks
+// kPyrRows output rows, so the per-pixel cost is 4 byte loads + the two fixed-point passes.
+constexpr int kPyrRows = 8;
 __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0) {
     const LevelGeom& d = g.lv[L];
     const LevelGeom& s = g.lv[L - 1];
     const int slot = slot0 + blockIdx.z;
     const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x4 >= d.w || y >= d.h) return;
+    if (x4 >= d.w) return;
     const uint32_t* tx = b.resizeTab + b.resizeTabOff[L][0];
     const uint32_t* ty = b.resizeTab + b.resizeTabOff[L][1];
     const uint8_t* src = b.pyr + (size_t)slot * g.slotStride + s.off;
     uint8_t* dst = b.pyr + (size_t)slot * g.slotStride + d.off;
-    const uint32_t ey = __ldg(ty + y);
-    const int oy = ey >> 16, cy1 = ey & 0xFFFF, cy0 = 256 - cy1;
-    const int oy1 = min(oy + 1, s.h - 1);
-    const uint8_t* r0 = src + (size_t)oy * s.pitch;
-    const uint8_t* r1 = src + (size_t)oy1 * s.pitch;
-    uint32_t out = 0;
+    int ox[4], ox1[4], cx1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int x = x4 + k;
-        if (x < d.w) {
-            const uint32_t ex = __ldg(tx + x);
-            const int ox = ex >> 16, cx1 = ex & 0xFFFF, cx0 = 256 - cx1;
-            const int ox1 = min(ox + 1, s.w - 1);
-            int h0 = cx0 * (int)__ldg(r0 + ox) + cx1 * (int)__ldg(r0 + ox1);
-            int h1 = cx0 * (int)__ldg(r1 + ox) + cx1 * (int)__ldg(r1 + ox1);
-            int v = (h0 * cy0 + h1 * cy1 + (1 << 15)) >> 16;
+        const uint32_t ex = __ldg(tx + min(x4 + k, d.w - 1));
+        ox[k] = ex >> 16;
+        cx1[k] = ex & 0xFFFF;
+        ox1[k] = min(ox[k] + 1, s.w - 1);
+    }
+    const int yBase = blockIdx.y * (8 * kPyrRows) + threadIdx.y;
+#pragma unroll 2
+    for (int r = 0; r < kPyrRows; ++r) {
+        const int y = yBase + 8 * r;
+        if (y >= d.h) break;
+        const uint32_t ey = __ldg(ty + y);
+        const int oy = ey >> 16, cy1 = ey & 0xFFFF, cy0 = 256 - cy1;
+        const int oy1 = min(oy + 1, s.h - 1);
+        const uint8_t* r0 = src + (size_t)oy * s.pitch;
+        const uint8_t* r1 = src + (size_t)oy1 * s.pitch;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cx0 = 256 - cx1[k];
+            const int h0 = cx0 * (int)__ldg(r0 + ox[k]) + cx1[k] * (int)__ldg(r0 + ox1[k]);
+            const int h1 = cx0 * (int)__ldg(r1 + ox[k]) + cx1[k] * (int)__ldg(r1 + ox1[k]);
+            const int v = (h0 * cy0 + h1 * cy1 + (1 << 15)) >> 16;
             out |= (uint32_t)v << (8 * k);
         }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x4) = out;
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x4) = out;
 }
 
 // =========================================================================================== A.2 FAST + NMS
@@ -865,7 +876,7 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     if (nSlots <= 0) return;
     cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
     for (int L = 1; L < g.nlevels; ++L) {
-        dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 7) / 8, nSlots);
+        dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 8 * kPyrRows - 1) / (8 * kPyrRows), nSlots);
         ProfScope ps_(PF_PYR, st);
         k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0);
         ++g_launches;

@@ -23,10 +23,14 @@ enum { RS_MAXGOOD = 0, RS_NITERS = 1, RS_DONE = 2, RS_BESTITER = 3, RS_BESTMODEL
 // registers, and the same distance feeds the column minimum through one redux.sync per (warp, train descriptor) on the
 // packed key (distance << 16 | queryIdx) -- so ties go to the lowest index on both sides, as cv2's batchDistance does.
 // Column keys are merged warp -> CTA (shared atomicMin) -> pair (global atomicMin); the launcher presets them to ~0.
+// kSplit (cross-check mode, no runner-up needed): the train descriptors are dealt out in 128-column tiles to gridDim.y
+// CTAs per query block, which multiplies the resident warps; row minima are then merged like the column minima, through
+// atomicMin on (distance << 16 | trainIdx) in nnIdx[dir 0].
+template <bool kSplit>
 __global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0) {
     __shared__ __align__(16) uint32_t tile[128 * 8];
     __shared__ uint32_t colmin[128];
-    const int pi = blockIdx.y;
+    const int pi = blockIdx.z;
     const int slotA = slotA0 + pi, slotB = slotA + 1;
     const int pair = pair0 + pi;
     const int nA = min(ob.featCount[slotA], pg.maxkp), nB = min(ob.featCount[slotB], pg.maxkp);
@@ -41,7 +45,8 @@ __global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom 
 #pragma unroll
     for (int w = 0; w < 8; ++w) q[w] = valid ? dA[(size_t)i * 8 + w] : 0u;
     int best = 0x7fffffff, bestIdx = -1, second = 0x7fffffff;
-    for (int j0 = 0; j0 < nB; j0 += 128) {
+    const uint32_t keyLow = valid ? (uint32_t)i : 0xFFFFFFFFu;     // rows past nA never win a column
+    for (int j0 = blockIdx.y * 128; j0 < nB; j0 += 128 * gridDim.y) {
         __syncthreads();
         // stage 128 train descriptors: 256 uint4
         for (int v = threadIdx.x; v < 256; v += 128) {
@@ -53,31 +58,36 @@ __global__ void __launch_bounds__(128) k_nn(OrbGeom og, OrbBuffers ob, PairGeom 
         colmin[threadIdx.x] = 0xFFFFFFFFu;
         __syncthreads();
         const int lim = min(128, nB - j0);
-        uint32_t mycol = 0xFFFFFFFFu;        // lane l: this warp's minimum for column (j & ~31) + l
-        for (int j = 0; j < lim; ++j) {
-            const uint4 t0 = reinterpret_cast<const uint4*>(tile)[j * 2];
-            const uint4 t1 = reinterpret_cast<const uint4*>(tile)[j * 2 + 1];
-            const int d = __popc(q[0] ^ t0.x) + __popc(q[1] ^ t0.y) + __popc(q[2] ^ t0.z) + __popc(q[3] ^ t0.w) +
-                          __popc(q[4] ^ t1.x) + __popc(q[5] ^ t1.y) + __popc(q[6] ^ t1.z) + __popc(q[7] ^ t1.w);
-            if (d < best) { second = best; best = d; bestIdx = j0 + j; }
-            else if (d < second) second = d;
-            const uint32_t key = valid ? (((uint32_t)d << 16) | (uint32_t)i) : 0xFFFFFFFFu;
-            const uint32_t m = __reduce_min_sync(0xffffffffu, key);
-            if (lane == (j & 31)) mycol = m;
-            if ((j & 31) == 31 || j == lim - 1) {
-                const int jj = (j & ~31) + lane;
-                if (jj <= j) atomicMin(&colmin[jj], mycol);
-                mycol = 0xFFFFFFFFu;
+        for (int jg = 0; jg < lim; jg += 32) {
+            uint32_t mycol = 0xFFFFFFFFu;    // lane l: this warp's minimum for column jg + l
+#pragma unroll 4
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = jg + jj;       // columns >= lim are zero-filled tile rows: computed, never used
+                const uint4 t0 = reinterpret_cast<const uint4*>(tile)[j * 2];
+                const uint4 t1 = reinterpret_cast<const uint4*>(tile)[j * 2 + 1];
+                const int d = (__popc(q[0] ^ t0.x) + __popc(q[1] ^ t0.y)) + (__popc(q[2] ^ t0.z) + __popc(q[3] ^ t0.w)) +
+                              ((__popc(q[4] ^ t1.x) + __popc(q[5] ^ t1.y)) + (__popc(q[6] ^ t1.z) + __popc(q[7] ^ t1.w)));
+                if (j < lim) {
+                    if (d < best) { second = best; best = d; bestIdx = j0 + j; }
+                    else if (d < second) second = d;
+                }
+                const uint32_t m = __reduce_min_sync(0xffffffffu, ((uint32_t)d << 16) | keyLow);
+                if (lane == jj) mycol = m;
             }
+            if (jg + lane < lim) atomicMin(&colmin[jg + lane], mycol);
         }
         __syncthreads();
         if (threadIdx.x < lim) atomicMin(&colKey[j0 + threadIdx.x], colmin[threadIdx.x]);
     }
     if (valid) {
         size_t o = (size_t)pair * 2 * pg.maxkp + i;
-        pb.nnIdx[o] = bestIdx;
-        pb.nnDist[o] = best;
-        pb.nn2Dist[(size_t)pair * pg.maxkp + i] = second;
+        if (kSplit) {
+            if (bestIdx >= 0) atomicMin(reinterpret_cast<uint32_t*>(pb.nnIdx) + o, ((uint32_t)best << 16) | (uint32_t)bestIdx);
+        } else {
+            pb.nnIdx[o] = bestIdx;
+            pb.nnDist[o] = best;
+            pb.nn2Dist[(size_t)pair * pg.maxkp + i] = second;
+        }
     }
 }
 
@@ -100,13 +110,16 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
     for (int i = tid; i < pg.sortCap; i += 1024) {
         uint32_t key = 0xFFFFFFFFu;
         if (i < nA && nB > 0) {
-            int j = fwd[i];
+            const bool packed = pg.matcher == DVO_MATCH_CROSSCHECK;     // k_nn<true> leaves (distance << 16 | trainIdx)
+            const uint32_t fk = (uint32_t)fwd[i];
+            const int j = packed ? (fk == 0xFFFFFFFFu ? -1 : (int)(fk & 0xFFFFu)) : fwd[i];
+            const int dist = packed ? (int)(fk >> 16) : fwdD[i];
             bool ok = j >= 0 && (int)(bwdKey[j] & 0xFFFFu) == i;
             if (pg.matcher == DVO_MATCH_KNN_RATIO) {
                 // knnMatch returns < 2 neighbours when the train set has one descriptor: the reference's unpacking needs two
-                ok = ok && nB >= 2 && ((double)fwdD[i] < (double)pg.ratio * (double)d2[i]);
+                ok = ok && nB >= 2 && ((double)dist < (double)pg.ratio * (double)d2[i]);
             }
-            if (ok) { key = ((uint32_t)fwdD[i] << 16) | (uint32_t)i; ++local; }
+            if (ok) { key = ((uint32_t)dist << 16) | (uint32_t)i; ++local; }
         }
         keys[i] = key;
     }
@@ -133,7 +146,8 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
     const size_t o = (size_t)pair * pg.maxkp;
     for (int r = tid; r < M; r += 1024) {
         uint32_t key = keys[r];
-        int i = key & 0xFFFF, d = key >> 16, j = fwd[i];
+        int i = key & 0xFFFF, d = key >> 16;
+        int j = pg.matcher == DVO_MATCH_CROSSCHECK ? (int)((uint32_t)fwd[i] & 0xFFFFu) : fwd[i];
         pb.matches[(o + r) * 3 + 0] = i;
         pb.matches[(o + r) * 3 + 1] = j;
         pb.matches[(o + r) * 3 + 2] = d;
@@ -449,7 +463,13 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
     {
         ProfScope ps_(PF_NN, st);
         cudaMemsetAsync(pb.nnIdx + (size_t)pair0 * 2 * pg.maxkp, 0xFF, sizeof(int) * 2 * (size_t)nPairs * pg.maxkp, st);
-        k_nn<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+        const int qBlocks = (pg.maxkp + 127) / 128;
+        if (pg.matcher == DVO_MATCH_CROSSCHECK) {
+            const int nSplit = qBlocks >= 4 ? 4 : 1;
+            k_nn<true><<<dim3(qBlocks, nSplit, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+        } else {
+            k_nn<false><<<dim3(qBlocks, 1, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
+        }
     }
     { ProfScope ps_(PF_SORT, st); k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy); }
     g_pair_launches += 2;
