@@ -156,7 +156,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -383,7 +383,25 @@ def run_b200(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # Libraries (NCCL's version banner, torchrun notices) may write to fd 1: keep stdout for the ONE JSON line by pointing
+    # fd 1 at stderr while the benchmark runs and restoring it just before printing.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _lines = []
+    _print = print
+
+    def print(*a, **k):        # noqa: A001  (collect the JSON line; emitted on the real stdout at the end)
+        _lines.append(" ".join(str(x) for x in a))
+
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        for ln in _lines:
+            _print(ln, flush=True)

@@ -364,6 +364,21 @@ DVO_HDN bool cheirality_ok(const double* R, const double* t, double x1, double y
     return m;
 }
 
+// Both translation signs from ONE triangulation.  For P1' = [R | -t] the DLT matrix is A with its 4th column negated;
+// one-sided Jacobi is sign-symmetric in a column (gamma, zeta, t and s flip sign together, every product is unchanged), so
+// its null vector is +-(X0, X1, X2, -X3) and the tests become: q' = -q, z2' = -z2 (exact IEEE negations).
+// Returns bit 0: (R, t) passes, bit 1: (R, -t) passes.
+DVO_HDN int cheirality_pair(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist) {
+    double Q[4];
+    triangulate_one(R, t, x1, y1, x2, y2, Q);
+    const double s = Q[2] * Q[3];
+    const double qx = Q[0] / Q[3], qy = Q[1] / Q[3], qz = Q[2] / Q[3];
+    const double z2 = R[6] * qx + R[7] * qy + R[8] * qz + t[2];
+    const bool mp = (s > 0) && (qz < dist) && (z2 > 0) && (z2 < dist);
+    const bool mn = (-s > 0) && (-qz < dist) && (-z2 > 0) && (-z2 < dist);
+    return (mp ? 1 : 0) | (mn ? 2 : 0);
+}
+
 // ---- Nister 5-point minimal solver -------------------------------------------------------------------------------
 // cubic monomial order (first ten are eliminated): x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1
 // linear terms: 0:x 1:y 2:z 3:1 ; quadratic monomials: 0:x2 1:xy 2:xz 3:x 4:y2 5:yz 6:y 7:z2 8:z 9:1

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
     __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
     __shared__ uint16_t list2[(kTileH + 2) * (kTileW + 2)];
-    __shared__ int s_n1, s_n2;
+    __shared__ int s_n1, s_n2, s_warpTot[8];
     __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
@@ -165,35 +165,46 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             if (rc >= 15 && rc <= 144 && sx >= 3 && sx < lv.w - 3) colmask |= 0x80u << (8 * k);
         }
         if (qrow >= kRowsPerSweep) colmask = 0;
-        for (int qy0 = 0; qy0 < kQuadsY; qy0 += kRowsPerSweep) {
-            const int qy = qy0 + qrow;
+        constexpr int kSweeps = (kQuadsY + kRowsPerSweep - 1) / kRowsPerSweep;
+        uint32_t passw[kSweeps];
+        int cnt = 0;
+#pragma unroll
+        for (int sw = 0; sw < kSweeps; ++sw) {
+            const int qy = sw * kRowsPerSweep + qrow;
             const int sy = y0 - 1 + qy;
             uint32_t pass = 0;
-            const int code0 = (qy + 3) * kFastBoxW + 12 + 4 * qx;
             if (colmask != 0 && qy < kQuadsY && sy >= 3 && sy < lv.h - 3) {
-                const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + code0);
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw + (qy + 3) * kFastBoxW + 12 + 4 * qx);
                 const uint32_t c = rp[0], lw = rp[-1], rw = rp[1];
                 const uint32_t up = rp[-3 * kRowWords], dn = rp[3 * kRowWords];
                 const uint32_t e = __byte_perm(c, rw, 0x6543), w = __byte_perm(lw, c, 0x4321);
                 pass = fast_prefilter_u8x4(c, up, e, dn, w, th) & colmask;
             }
-            // warp-aggregated append (exclusive scan of the per-thread counts)
-            const int cnt = __popc(pass);
-            int incl = cnt;
+            passw[sw] = pass;
+            cnt += __popc(pass);
+        }
+        // one CTA-wide exclusive scan of the per-thread survivor counts, then every thread appends its own survivors
+        int incl = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            int base = 0;
-            if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            if (pass) {
-                int pos = base + incl - cnt;
-                if (pass & 0x00000080u) list1[pos++] = (uint16_t)(code0);
-                if (pass & 0x00008000u) list1[pos++] = (uint16_t)(code0 + 1);
-                if (pass & 0x00800000u) list1[pos++] = (uint16_t)(code0 + 2);
-                if (pass & 0x80000000u) list1[pos] = (uint16_t)(code0 + 3);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warpTot[tid >> 5] = incl;
+        __syncthreads();
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) base += (w < (tid >> 5)) ? s_warpTot[w] : 0;
+        if (tid == 255) s_n1 = base + incl;
+        int pos = base + incl - cnt;
+#pragma unroll
+        for (int sw = 0; sw < kSweeps; ++sw) {
+            uint32_t m = passw[sw];
+            const int code0 = (sw * kRowsPerSweep + qrow + 3) * kFastBoxW + 12 + 4 * qx;
+            while (m) {
+                const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
+                list1[pos++] = (uint16_t)(code0 + (bit >> 3));
+                m &= m - 1;
             }
         }
     }

@@ -338,19 +338,18 @@ __global__ void __launch_bounds__(128) k_cheirality(PairGeom pg, PairBuffers pb,
     const int M = pb.matchCount[pair];
     if (blockIdx.x * 128 >= M) return;
     PoseScratch& sc = ps[pair];
-    __shared__ double sR1[9], sR2[9], st[3], snt[3];
+    __shared__ double sR1[9], sR2[9], st[3];
     if (threadIdx.x < 9) { sR1[threadIdx.x] = sc.R1[threadIdx.x]; sR2[threadIdx.x] = sc.R2[threadIdx.x]; }
-    if (threadIdx.x < 3) { st[threadIdx.x] = sc.t[threadIdx.x]; snt[threadIdx.x] = -sc.t[threadIdx.x]; }
+    if (threadIdx.x < 3) st[threadIdx.x] = sc.t[threadIdx.x];
     __syncthreads();
     const int i = blockIdx.x * 128 + threadIdx.x;
     int flags = 0;
     if (i < M) {
         const double* p = pb.normPts + ((size_t)pair * pg.maxkp + i) * 4;
         double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
-        flags |= cheirality_ok(sR1, st, x1, y1, x2, y2, pg.distThresh) ? 1 : 0;
-        flags |= cheirality_ok(sR2, st, x1, y1, x2, y2, pg.distThresh) ? 2 : 0;
-        flags |= cheirality_ok(sR1, snt, x1, y1, x2, y2, pg.distThresh) ? 4 : 0;
-        flags |= cheirality_ok(sR2, snt, x1, y1, x2, y2, pg.distThresh) ? 8 : 0;
+        const int a = cheirality_pair(sR1, st, x1, y1, x2, y2, pg.distThresh);     // candidates 0 (R1, t) and 2 (R1, -t)
+        const int c = cheirality_pair(sR2, st, x1, y1, x2, y2, pg.distThresh);     // candidates 1 (R2, t) and 3 (R2, -t)
+        flags = (a & 1) | ((c & 1) << 1) | ((a & 2) << 1) | ((c & 2) << 2);
         pb.poseMask[(size_t)pair * pg.maxkp + i] = (uint8_t)flags;
     }
 #pragma unroll

@@ -131,6 +131,9 @@ void hs_decompose(const double* E, double* R1, double* R2, double* t) { decompos
 int hs_cheirality(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist) {
     return cheirality_ok(R, t, x1, y1, x2, y2, dist) ? 1 : 0;
 }
+int hs_cheirality_pair(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist) {
+    return cheirality_pair(R, t, x1, y1, x2, y2, dist);
+}
 void hs_triangulate(const double* R, const double* t, double x1, double y1, double x2, double y2, double* X) {
     triangulate_one(R, t, x1, y1, x2, y2, X);
 }

@@ -176,3 +176,18 @@ def test_sampson_inlier_shortcut_equals_exact_decision(hostsim, golden):
                 continue
             got = hostsim.hs_sampson_inlier(ptr(E), float(a[0]), float(a[1]), float(b[0]), float(b[1]), float(t))
             assert got == int(errs[i] <= t)
+
+
+def test_cheirality_pair_equals_two_separate_triangulations(hostsim, golden):
+    """one triangulation serves (R, t) and (R, -t): same decisions as triangulating both"""
+    hostsim.hs_cheirality_pair.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 5
+    Rg, tg = np.ascontiguousarray(golden["c5_R"]), np.ascontiguousarray(golden["c5_t"].ravel())
+    tn = np.ascontiguousarray(-tg)
+    x1 = P.normalize_points(golden["c5_p1"], golden["c5_K"]); x2 = P.normalize_points(golden["c5_p2"], golden["c5_K"])
+    bad = 0
+    for a, b in zip(x1[:1500], x2[:1500]):
+        args = (float(a[0]), float(a[1]), float(b[0]), float(b[1]), 50.0)
+        both = hostsim.hs_cheirality_pair(ptr(Rg), ptr(tg), *args)
+        sep = hostsim.hs_cheirality(ptr(Rg), ptr(tg), *args) | (hostsim.hs_cheirality(ptr(Rg), ptr(tn), *args) << 1)
+        bad += int(both != sep)
+    assert bad == 0
