@@ -239,12 +239,14 @@ def run_b200(a):
 
     # ---- warm-up (also primes the carry slot so every timed step is B pairs)
     device_pass(0, W_steps, fresh=True)
+    ctx.flush()
     barrier()
     launches0 = ctx.kernel_launches
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     npairs = device_pass(W_steps, K_steps, fresh=False)
+    ctx.flush()     # join torch's stream with the pipelined runner's internal streams before the closing event
     if world > 1:   # the path's one exchange step: all-gather of the per-pair (R, t, status) records
         dist.all_gather_into_tensor(gathered, poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec])
     ev1.record()

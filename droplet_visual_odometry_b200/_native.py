@@ -27,7 +27,7 @@ class dvo_config(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int),
                 ("fast_threshold", ctypes.c_int), ("max_frames", ctypes.c_int), ("matcher", ctypes.c_int),
                 ("ransac_max_iters", ctypes.c_int), ("ransac_prob", ctypes.c_double), ("ransac_threshold", ctypes.c_double),
-                ("distance_thresh", ctypes.c_double), ("ratio", ctypes.c_float), ("use_tma", ctypes.c_int)]
+                ("distance_thresh", ctypes.c_double), ("ratio", ctypes.c_float), ("use_tma", ctypes.c_int), ("pipeline", ctypes.c_int)]
 
 
 class dvo_features(ctypes.Structure):
@@ -80,6 +80,7 @@ def load_library():
     lib.dvo_get_pair_arrays.argtypes = [vp, ci, ctypes.POINTER(dvo_pair_arrays), vp]
     lib.dvo_sequence.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, vp]
     lib.dvo_sequence_step.argtypes = [vp, vp, ci, cs, cs, vp, vp, ci, ci, vp]
+    lib.dvo_sequence_flush.argtypes = [vp, vp]
     lib.dvo_profile_enable.argtypes = [ci]
     lib.dvo_profile_enable.restype = None
     lib.dvo_profile_collect.argtypes = [vp, vp, ci]
@@ -106,7 +107,7 @@ class Context:
 
     def __init__(self, width, height, nfeatures=500, nlevels=8, max_frames=2, matcher=DVO_MATCH_CROSSCHECK,
                  ransac_max_iters=1000, ransac_prob=0.999, ransac_threshold=1.0, distance_thresh=50.0, ratio=0.75,
-                 fast_threshold=20, device=0, use_tma=True):
+                 fast_threshold=20, device=0, use_tma=True, pipeline=True):
         self.lib = load_library()
         self.torch = _torch()
         cfg = dvo_config()
@@ -115,6 +116,7 @@ class Context:
         cfg.max_frames, cfg.matcher, cfg.ransac_max_iters = int(max_frames), int(matcher), int(ransac_max_iters)
         cfg.ransac_prob, cfg.ransac_threshold, cfg.distance_thresh = float(ransac_prob), float(ransac_threshold), float(distance_thresh)
         cfg.ratio, cfg.fast_threshold, cfg.use_tma = float(ratio), int(fast_threshold), int(bool(use_tma))
+        cfg.pipeline = int(bool(pipeline))
         self.cfg = cfg
         self.device = int(device)
         self.width, self.height, self.nlevels = int(width), int(height), int(nlevels)
@@ -150,7 +152,12 @@ class Context:
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.tdev).cuda_stream)
 
+    def flush(self):
+        """Join torch's current stream with the pipelined sequence runner's internal streams (dvo_sequence_flush)."""
+        self._check(self.lib.dvo_sequence_flush(self._h, self._stream()), "dvo_sequence_flush")
+
     def sync(self):
+        self.flush()
         self.torch.cuda.current_stream(self.tdev).synchronize()
 
     @property

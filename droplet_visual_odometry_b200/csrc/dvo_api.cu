@@ -36,6 +36,18 @@ struct dvo_ctx {
     long long launchBase = 0;
     int carrySlot = -1;                // slot holding the last frame of the previous dvo_sequence_step
     SideStreams ss;
+    // Two-lane sequence pipeline (cfg.pipeline): lane 1 is a second set of ORB buffers so that the ORB stage of batch
+    // s+1 (stream sOrb) runs while the pair stage of batch s (stream sPair) still reads batch s's features.
+    OrbBuffers ob1{};
+    TensorMaps tmaps1{};
+    bool lane1Ready = false;
+    std::vector<void*> lane1Allocs;
+    cudaStream_t sOrb = nullptr, sPair = nullptr;
+    cudaEvent_t evCall = nullptr, evOrbDone[2] = {nullptr, nullptr}, evPairsDone[2] = {nullptr, nullptr},
+                evCarryCopied[2] = {nullptr, nullptr};
+    bool pairsPending[2] = {false, false}, carryPending[2] = {false, false};
+    int carryLane = 0, lastLane = -1;
+    bool pipeOutstanding = false;      // sPair holds work the caller's stream has not been joined with yet
 };
 
 #define CK(call)                                                                                     \
@@ -61,6 +73,35 @@ static int dalloc(dvo_ctx* ctx, T** p, size_t count) {
     cudaMemset(q, 0, bytes);
     ctx->allocs.push_back(q);
     *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+static int alloc_orb_buffers(dvo_ctx* ctx, OrbBuffers& b) {
+    const OrbGeom& g = ctx->og;
+    const size_t S = ctx->nSlots;
+    int rc;
+#define DA(p, n) if ((rc = dalloc(ctx, &(p), (n))) != 0) return rc
+    DA(b.pyr, S * g.slotStride + 4096);
+    DA(b.blur, S * g.slotStride + 4096);
+    DA(b.map, S * g.slotStride + 4096);
+    DA(b.rowCount, S * g.rowsPerSlot);
+    DA(b.cand, S * g.candPerSlot);
+    DA(b.candCount, S * kMaxLevels);
+    DA(b.pairs, S * g.candPerSlot);
+    DA(b.selWork, S * g.candPerSlot);
+    DA(b.selList, S * g.candPerSlot * 2);
+    DA(b.finXY, S * g.finPerSlot);
+    DA(b.finResp, S * g.finPerSlot);
+    DA(b.finCount, S * kMaxLevels);
+    DA(b.selDbg, S * kMaxLevels * 4);
+    DA(b.featPt, S * g.maxkp * 2);
+    DA(b.featResp, S * g.maxkp);
+    DA(b.featAngle, S * g.maxkp);
+    DA(b.featOctave, S * g.maxkp);
+    DA(b.featXY, S * g.maxkp);
+    DA(b.featDesc, S * g.maxkp * 32);
+    DA(b.featCount, S);
+#undef DA
     return 0;
 }
 
@@ -143,7 +184,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int build_tensor_maps(dvo_ctx* ctx) {
+static int build_tensor_maps(dvo_ctx* ctx, const OrbBuffers& ob, TensorMaps& tmaps) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -158,7 +199,7 @@ static int build_tensor_maps(dvo_ctx* ctx) {
         cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)ctx->og.slotStride};
         cuuint32_t box[3] = {(cuuint32_t)kFastBoxW, (cuuint32_t)kFastBoxH, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&ctx->tmaps.pyr[L], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->ob.pyr + lv.off, dims, strides, box, estr,
+        CUresult r = encode(&tmaps.pyr[L], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ob.pyr + lv.off, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -192,7 +233,7 @@ void dvo_default_config(dvo_config* c) {
     c->max_frames = 2;
     c->matcher = DVO_MATCH_CROSSCHECK;
     c->ransac_max_iters = 1000; c->ransac_prob = 0.999; c->ransac_threshold = 1.0;
-    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1;
+    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1; c->pipeline = 1;
 }
 
 int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
@@ -214,29 +255,9 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     build_geometry(ctx);
     OrbGeom& g = ctx->og;
     OrbBuffers& b = ctx->ob;
-    const size_t S = ctx->nSlots;
     int rc;
 #define DA(p, n) if ((rc = dalloc(ctx, &(p), (n))) != 0) return rc
-    DA(b.pyr, S * g.slotStride + 4096);
-    DA(b.blur, S * g.slotStride + 4096);
-    DA(b.map, S * g.slotStride + 4096);
-    DA(b.rowCount, S * g.rowsPerSlot);
-    DA(b.cand, S * g.candPerSlot);
-    DA(b.candCount, S * kMaxLevels);
-    DA(b.pairs, S * g.candPerSlot);
-    DA(b.selWork, S * g.candPerSlot);
-    DA(b.selList, S * g.candPerSlot * 2);
-    DA(b.finXY, S * g.finPerSlot);
-    DA(b.finResp, S * g.finPerSlot);
-    DA(b.finCount, S * kMaxLevels);
-    DA(b.selDbg, S * kMaxLevels * 4);
-    DA(b.featPt, S * g.maxkp * 2);
-    DA(b.featResp, S * g.maxkp);
-    DA(b.featAngle, S * g.maxkp);
-    DA(b.featOctave, S * g.maxkp);
-    DA(b.featXY, S * g.maxkp);
-    DA(b.featDesc, S * g.maxkp * 32);
-    DA(b.featCount, S);
+    if ((rc = alloc_orb_buffers(ctx, b)) != 0) return rc;
     // resize tables
     {
         std::vector<uint32_t> tab;
@@ -285,7 +306,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
 #undef DA
     ctx->useTma = cfg->use_tma != 0 && getenv("DVO_NO_TMA") == nullptr;
     if (ctx->useTma) {
-        rc = build_tensor_maps(ctx);
+        rc = build_tensor_maps(ctx, ctx->ob, ctx->tmaps);
         if (rc != 0) return rc;
     }
     if (getenv("DVO_NO_SIDE_STREAMS") == nullptr) {
@@ -296,6 +317,16 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&ctx->ss.evCopied[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->ss.evStageFree[i], cudaEventDisableTiming));
+        }
+    }
+    if (cfg->pipeline != 0 && getenv("DVO_NO_PIPELINE") == nullptr) {
+        CK(cudaStreamCreateWithFlags(&ctx->sOrb, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->sPair, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->evCall, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->evOrbDone[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->evPairsDone[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->evCarryCopied[i], cudaEventDisableTiming));
         }
     }
     orb_kernels_init();
@@ -310,6 +341,14 @@ void dvo_destroy(dvo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->evCall) cudaEventDestroy(ctx->evCall);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->evOrbDone[i]) cudaEventDestroy(ctx->evOrbDone[i]);
+        if (ctx->evPairsDone[i]) cudaEventDestroy(ctx->evPairsDone[i]);
+        if (ctx->evCarryCopied[i]) cudaEventDestroy(ctx->evCarryCopied[i]);
+    }
+    if (ctx->sOrb) cudaStreamDestroy(ctx->sOrb);
+    if (ctx->sPair) cudaStreamDestroy(ctx->sPair);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ss.stage[i]) cudaFree(ctx->ss.stage[i]);
         if (ctx->ss.evCopied[i]) cudaEventDestroy(ctx->ss.evCopied[i]);
@@ -339,24 +378,31 @@ int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota) {
     return DVO_OK;
 }
 
+static int load_frames_into(dvo_ctx* ctx, const OrbBuffers& ob, const uint8_t* frames, int n, size_t pitch, size_t frame_stride,
+                            int slot0, int kind, cudaStream_t st);
+
 int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, size_t frame_stride, int slot0, int kind,
                     void* stream) {
     if (!ctx || !frames || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots || pitch < (size_t)ctx->cfg.width) {
         if (ctx) ctx->err = "dvo_load_frames: bad arguments";
         return DVO_E_INVALID;
     }
-    cudaStream_t st = (cudaStream_t)stream;
+    return load_frames_into(ctx, ctx->ob, frames, n, pitch, frame_stride, slot0, kind, (cudaStream_t)stream);
+}
+
+static int load_frames_into(dvo_ctx* ctx, const OrbBuffers& ob, const uint8_t* frames, int n, size_t pitch, size_t frame_stride,
+                            int slot0, int kind, cudaStream_t st) {
     const LevelGeom& l0 = ctx->og.lv[0];
     if (n == 0) return DVO_OK;
     if (kind == 0) {
-        launch_load_frames(ctx->og, ctx->ob, frames, n, pitch, frame_stride, slot0, st);
+        launch_load_frames(ctx->og, ob, frames, n, pitch, frame_stride, slot0, st);
         CK(cudaGetLastError());
         return DVO_OK;
     }
     SideStreams& ss = ctx->ss;
     if (ss.copy == nullptr) {   // side streams disabled: plain in-order copies
         for (int i = 0; i < n; ++i) {
-            CK(cudaMemcpy2DAsync(ctx->ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
+            CK(cudaMemcpy2DAsync(ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
                                  frames + (size_t)i * frame_stride, pitch, l0.w, l0.h, cudaMemcpyHostToDevice, st));
         }
         return DVO_OK;
@@ -377,7 +423,7 @@ int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, si
     }
     CK(cudaEventRecord(ss.evCopied[bsel], ss.copy));
     CK(cudaStreamWaitEvent(st, ss.evCopied[bsel], 0));
-    launch_load_frames(ctx->og, ctx->ob, ss.stage[bsel], n, l0.w, frameBytes, slot0, st);
+    launch_load_frames(ctx->og, ob, ss.stage[bsel], n, l0.w, frameBytes, slot0, st);
     CK(cudaEventRecord(ss.evStageFree[bsel], st));
     ss.stageUsed[bsel] = true;
     CK(cudaGetLastError());
@@ -524,21 +570,99 @@ int dvo_tap_ransac(dvo_ctx* ctx, int pair, int32_t* h_state8, void* stream) {
     return DVO_OK;
 }
 
-__global__ void k_copy_features(OrbGeom g, OrbBuffers b, int src, int dst) {
-    // carry the last frame of a batch into slot 0 for the next batch
+__global__ void k_copy_features(OrbGeom g, OrbBuffers a, OrbBuffers b, int src, int dst) {
+    // carry the last frame of a batch (buffers a, slot src) into slot dst of buffers b for the next batch
     const int M = g.maxkp;
     const size_t so = (size_t)src * M, d0 = (size_t)dst * M;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * 8; i += gridDim.x * blockDim.x) {
-        reinterpret_cast<uint32_t*>(b.featDesc + d0 * 32)[i] = reinterpret_cast<const uint32_t*>(b.featDesc + so * 32)[i];
-        if (i < M * 2) b.featPt[d0 * 2 + i] = b.featPt[so * 2 + i];
+        reinterpret_cast<uint32_t*>(b.featDesc + d0 * 32)[i] = reinterpret_cast<const uint32_t*>(a.featDesc + so * 32)[i];
+        if (i < M * 2) b.featPt[d0 * 2 + i] = a.featPt[so * 2 + i];
         if (i < M) {
-            b.featResp[d0 + i] = b.featResp[so + i];
-            b.featAngle[d0 + i] = b.featAngle[so + i];
-            b.featOctave[d0 + i] = b.featOctave[so + i];
-            b.featXY[d0 + i] = b.featXY[so + i];
+            b.featResp[d0 + i] = a.featResp[so + i];
+            b.featAngle[d0 + i] = a.featAngle[so + i];
+            b.featOctave[d0 + i] = a.featOctave[so + i];
+            b.featXY[d0 + i] = a.featXY[so + i];
         }
-        if (i == 0) b.featCount[dst] = b.featCount[src];
+        if (i == 0) b.featCount[dst] = a.featCount[src];
     }
+}
+
+// Two-lane pipeline.  Per call: ORB of this batch on sOrb into lane L = (previous lane ^ 1); pair stage on sPair after it.
+// Hazards and the events that order them:
+//   ORB(L) overwrites lane L's features       -> waits evPairsDone[L] (pairs of the batch before last) and
+//                                                evCarryCopied[L] (the carry copy out of lane L issued with the last batch)
+//   carry copy  last slot of lane L^1 -> slot 0 of lane L runs on sPair after the previous pair stage (stream order)
+//   pairs(L) needs ORB(L)                      -> sPair waits evOrbDone[L]
+// The caller's stream is joined with the PREVIOUS batch's pair stage only (so consecutive calls overlap); the current
+// batch's pose records are complete once the next call, or dvo_sequence_flush, has been enqueued on that stream.
+static int sequence_step_pipelined(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pitch, size_t frame_stride, const double* K,
+                                   dvo_pose* poses, int kind, int first, cudaStream_t st) {
+    const bool fresh = first || ctx->carrySlot < 0 || ctx->lastLane < 0;
+    if (fresh ? n_new > ctx->nSlots : n_new > ctx->nSlots - 1) {
+        ctx->err = "dvo_sequence_step: more frames than slots";
+        return DVO_E_CAPACITY;
+    }
+    const int L = fresh ? 0 : (ctx->lastLane ^ 1);
+    int rc;
+    if (L == 1 && !ctx->lane1Ready) {
+        size_t mark = ctx->allocs.size();
+        if ((rc = alloc_orb_buffers(ctx, ctx->ob1)) != 0) return rc;
+        (void)mark;
+        ctx->ob1.resizeTab = ctx->ob.resizeTab;
+        memcpy(ctx->ob1.resizeTabOff, ctx->ob.resizeTabOff, sizeof(ctx->ob.resizeTabOff));
+        if (ctx->useTma && (rc = build_tensor_maps(ctx, ctx->ob1, ctx->tmaps1)) != 0) return rc;
+        CK(cudaDeviceSynchronize());
+        ctx->lane1Ready = true;
+    }
+    const OrbBuffers& ob = L == 0 ? ctx->ob : ctx->ob1;
+    const TensorMaps& tm = L == 0 ? ctx->tmaps : ctx->tmaps1;
+    const int slot0 = fresh ? 0 : 1, nPairs = fresh ? n_new - 1 : n_new;
+    // ---- ORB stage
+    CK(cudaEventRecord(ctx->evCall, st));
+    CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCall, 0));
+    if (ctx->pairsPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evPairsDone[L], 0));
+    if (ctx->carryPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCarryCopied[L], 0));
+    if ((rc = load_frames_into(ctx, ob, frames, n_new, pitch, frame_stride, slot0, kind, ctx->sOrb)) != 0) return rc;
+    launch_orb(ctx->og, ob, &tm, ctx->useTma, slot0, n_new, ctx->sOrb, &ctx->ss);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->evOrbDone[L], ctx->sOrb));
+    // ---- pair stage
+    CK(cudaStreamWaitEvent(ctx->sPair, ctx->evOrbDone[L], 0));
+    if (!fresh) {
+        const OrbBuffers& prev = ctx->carryLane == 0 ? ctx->ob : ctx->ob1;
+        k_copy_features<<<32, 256, 0, ctx->sPair>>>(ctx->og, prev, ob, ctx->carrySlot, 0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->evCarryCopied[ctx->carryLane], ctx->sPair));
+        ctx->carryPending[ctx->carryLane] = true;
+    }
+    if (nPairs > 0) {
+        if (ctx->pg.sortCap * sizeof(uint32_t) > 200 * 1024) {
+            ctx->err = "dvo_sequence_step: nfeatures too large for the in-shared-memory match sort";
+            return DVO_E_CAPACITY;
+        }
+        launch_pairs(ctx->og, ob, ctx->pg, ctx->pb, 0, 0, nPairs, K, ctx->sPair);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(poses, ctx->pb.poses, sizeof(dvo_pose) * nPairs, kind == 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           ctx->sPair));
+    }
+    CK(cudaEventRecord(ctx->evPairsDone[L], ctx->sPair));
+    ctx->pairsPending[L] = true;
+    // ---- deferred join: the caller's stream waits for the batch before this one
+    if (!fresh && ctx->pairsPending[L ^ 1]) CK(cudaStreamWaitEvent(st, ctx->evPairsDone[L ^ 1], 0));
+    ctx->pipeOutstanding = true;
+    ctx->lastLane = L;
+    ctx->carryLane = L;
+    ctx->carrySlot = fresh ? n_new - 1 : n_new;
+    return nPairs;
+}
+
+int dvo_sequence_flush(dvo_ctx* ctx, void* stream) {
+    if (!ctx) return DVO_E_INVALID;
+    if (ctx->sOrb != nullptr && ctx->pipeOutstanding && ctx->lastLane >= 0) {
+        CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->evPairsDone[ctx->lastLane], 0));
+        ctx->pipeOutstanding = false;
+    }
+    return DVO_OK;
 }
 
 int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pitch, size_t frame_stride, const double* K,
@@ -549,6 +673,7 @@ int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pit
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (ctx->sOrb != nullptr) return sequence_step_pipelined(ctx, frames, n_new, pitch, frame_stride, K, poses, kind, first, st);
     if (first || ctx->carrySlot < 0) {
         if (n_new > ctx->nSlots) { ctx->err = "dvo_sequence_step: more frames than slots"; return DVO_E_CAPACITY; }
         if ((rc = dvo_load_frames(ctx, frames, n_new, pitch, frame_stride, 0, kind, st)) != 0) return rc;
@@ -562,7 +687,7 @@ int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pit
     }
     if (n_new > ctx->nSlots - 1) { ctx->err = "dvo_sequence_step: more new frames than slots - 1"; return DVO_E_CAPACITY; }
     if (ctx->carrySlot != 0) {
-        k_copy_features<<<32, 256, 0, st>>>(ctx->og, ctx->ob, ctx->carrySlot, 0);
+        k_copy_features<<<32, 256, 0, st>>>(ctx->og, ctx->ob, ctx->ob, ctx->carrySlot, 0);
         CK(cudaGetLastError());
     }
     if ((rc = dvo_load_frames(ctx, frames, n_new, pitch, frame_stride, 1, kind, st)) != 0) return rc;
@@ -589,6 +714,7 @@ int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch
         if (rc < 0) return rc;
         done += nb;
     }
+    if ((rc = dvo_sequence_flush(ctx, stream)) != 0) return rc;
     if (kind == 1) CK(cudaStreamSynchronize((cudaStream_t)stream));
     return DVO_OK;
 }

@@ -90,7 +90,8 @@ DVO_HD int imin(int a, int b) { return a < b ? a : b; }
 DVO_HD int imax(int a, int b) { return a > b ? a : b; }
 
 // Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
-DVO_HD bool fast_is_corner16(int v, const int* p, int t) {
+// Returns the passing polarities: bit 0 = a 9-arc with every d > t, bit 1 = a 9-arc with every d < -t (0 = not a corner).
+DVO_HD int fast_corner_polarity16(int v, const int* p, int t) {
     // bit per ring pixel, shifted in at the bottom (ring order reversed -- contiguity is what matters):
     // sign(p - lo) <=> p < v - t <=> d > t ;  sign(hi - p) <=> p > v + t <=> d < -t
     uint32_t brighter = 0, darker = 0;
@@ -105,21 +106,24 @@ DVO_HD bool fast_is_corner16(int v, const int* p, int t) {
         darker = (darker << 1) | ((uint32_t)(hi - p[k]) >> 31);
 #endif
     }
-    return ring_has9(brighter) || ring_has9(darker);
+    return (ring_has9(brighter) ? 1 : 0) | (ring_has9(darker) ? 2 : 0);
 }
+DVO_HD bool fast_is_corner16(int v, const int* p, int t) { return fast_corner_polarity16(v, p, t) != 0; }
 
 // Score of a pixel already known to be a corner at threshold t: m-1 where m = max over the 16 arcs of
 // max(min(d), min(-d)), d_k = v - p_k  (m > t  <=>  corner).  The arc maximum is evaluated pairwise (two 9-arcs share an
 // 8-arc), starting the running bound at t.
 // (A straightforward 16x9 min/max double loop was miscompiled by nvcc 12.9 for sm_100a -- returned max(d) -- so this
 // formulation is deliberate; tests/test_gpu_* check it against the oracle on every level.)
-DVO_HD int fast_corner_score16(int v, const int* p, int t) {
+// `pol` (fast_corner_polarity16) lets the loop of a polarity without a passing arc be skipped: it could not move its bound.
+DVO_HD int fast_corner_score16(int v, const int* p, int t, int pol = 3) {
     int d[25];
 #pragma unroll
     for (int k = 0; k < 16; ++k) d[k] = v - p[k];
 #pragma unroll
     for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
     int a0 = t;
+    if (pol & 1)
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
         int a = imin(imin(d[k + 1], d[k + 2]), d[k + 3]);
@@ -129,6 +133,7 @@ DVO_HD int fast_corner_score16(int v, const int* p, int t) {
         a0 = imax(a0, imin(a, d[k + 9]));
     }
     int b0 = -a0;
+    if (pol & 2)
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
         int b = imax(imax(d[k + 1], d[k + 2]), d[k + 3]);
@@ -142,7 +147,8 @@ DVO_HD int fast_corner_score16(int v, const int* p, int t) {
 
 // Corner score of one pixel given centre value v and the 16 ring values; 0 if not a corner at threshold t.
 DVO_HD int fast_score16(int v, const int* p, int t) {
-    return fast_is_corner16(v, p, t) ? fast_corner_score16(v, p, t) : 0;
+    const int pol = fast_corner_polarity16(v, p, t);
+    return pol ? fast_corner_score16(v, p, t, pol) : 0;
 }
 
 // Packed prefilter on 4 horizontally adjacent pixels (one per byte): c = centres, n/e/s/w = the compass ring points

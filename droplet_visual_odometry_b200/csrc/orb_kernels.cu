@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     const int n1 = s_n1;
     for (int i0 = 0; i0 < n1; i0 += 256) {
         const int i = i0 + tid;
-        bool corner = false;
+        int pol = 0;
         int code = 0;
         if (i < n1) {
             code = list1[i];
@@ -223,13 +223,14 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             int pr[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
-            corner = fast_is_corner16(*c, pr, th);
+            pol = fast_corner_polarity16(*c, pr, th);
         }
+        const bool corner = pol != 0;
         const unsigned m = __ballot_sync(0xffffffffu, corner);
         int base = 0;
         if (lane == 0 && m) base = atomicAdd(&s_n2, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)code;
+        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
     }
     __syncthreads();
 
@@ -239,20 +240,20 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     if (tid < kTileH) s_rowcnt[tid] = 0;
     const int n2 = s_n2;
     for (int i = tid; i < n2; i += 256) {
-        const int code = list2[i];
+        const int code = list2[i] & 0x1FFF, pol = list2[i] >> 13;
         const uint8_t* c = raw + code;
         int pr[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
         const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
-        sc[(ry - 3) * 136 + (rx - 15)] = (uint8_t)fast_corner_score16(*c, pr, th);
+        sc[(ry - 3) * 136 + (rx - 15)] = (uint8_t)fast_corner_score16(*c, pr, th, pol);
     }
     __syncthreads();
 
     // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull
     const int border = 31;
     for (int i = tid; i < n2; i += 256) {
-        const int code = list2[i];
+        const int code = list2[i] & 0x1FFF;
         const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
         const int cy = ry - 3, cx = rx - 15;                   // ring coordinates: tile pixel (cx-1, cy-1)
         const int x = x0 + cx - 1, y = y0 + cy - 1;

@@ -55,6 +55,9 @@ typedef struct dvo_config {
     double distance_thresh;  /* cv.recoverPose distanceThresh, cv2 default 50                              */
     float ratio;             /* 0.75   (visual_odometry_v3.py:227)                                         */
     int use_tma;             /* 1: stage FAST tiles with TMA (default); 0: plain loads (debug)             */
+    int pipeline;            /* 1 (default): dvo_sequence / dvo_sequence_step overlap the ORB stage of one batch with the
+                                pair stage of the previous one on internal streams (second buffer set, allocated on
+                                first use); 0: every stage in order on the caller's stream                        */
 } dvo_config;
 
 /* Result of one frame pair: what cv.findEssentialMat + cv.recoverPose return (visual_odometry_v3.py:297-306). */
@@ -144,9 +147,15 @@ int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch
 
 /* One batch of a longer sequence: `first` != 0 starts a sequence (n_new frames -> n_new-1 pairs); otherwise the last
  * frame of the previous call is carried (its features are kept, not recomputed) and n_new frames give n_new pairs.
- * Returns the number of pose records written (>= 0) or a negative error.  Asynchronous for device memory. */
+ * Returns the number of pose records written (>= 0) or a negative error.  Asynchronous; see dvo_sequence_flush. */
 int dvo_sequence_step(dvo_ctx* ctx, const uint8_t* frames, int n_new, size_t pitch, size_t frame_stride, const double* K,
                       dvo_pose* poses, int kind, int first, void* stream);
+
+/* With cfg.pipeline = 1 the pose records written by a dvo_sequence_step call are complete once the NEXT
+ * dvo_sequence_step call, or this flush, has been enqueued and `stream` has reached that point.  dvo_sequence flushes by
+ * itself.  A no-op without the pipeline.  Also call it before using the per-stage entry points (dvo_orb, dvo_pairs, taps)
+ * after a pipelined sequence. */
+int dvo_sequence_flush(dvo_ctx* ctx, void* stream);
 
 /* Per-kernel CUDA-event timing for the roofline report (process-wide switch; collect synchronises the device and
  * returns the number of kernel ids; ms/count are totals since the previous collect). */
