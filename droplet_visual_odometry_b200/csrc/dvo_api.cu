@@ -12,6 +12,7 @@ long long pair_launch_count();
 void orb_kernels_init();
 void pair_kernels_init(int sortBytes);
 void prof_enable(bool on);
+bool prof_enabled();
 void prof_collect(double* ms, int* count, int n);
 }  // namespace dvo
 
@@ -311,7 +312,10 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     }
     if (getenv("DVO_NO_SIDE_STREAMS") == nullptr) {
         CK(cudaStreamCreateWithFlags(&ctx->ss.side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->ss.side2, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->ss.copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ss.evFork2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ss.evJoin2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ss.evFork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ss.evJoin, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
@@ -356,6 +360,9 @@ void dvo_destroy(dvo_ctx* ctx) {
     }
     if (ctx->ss.evFork) cudaEventDestroy(ctx->ss.evFork);
     if (ctx->ss.evJoin) cudaEventDestroy(ctx->ss.evJoin);
+    if (ctx->ss.evFork2) cudaEventDestroy(ctx->ss.evFork2);
+    if (ctx->ss.evJoin2) cudaEventDestroy(ctx->ss.evJoin2);
+    if (ctx->ss.side2) cudaStreamDestroy(ctx->ss.side2);
     if (ctx->ss.side) cudaStreamDestroy(ctx->ss.side);
     if (ctx->ss.copy) cudaStreamDestroy(ctx->ss.copy);
     if (ctx->h_poseStage) cudaFreeHost(ctx->h_poseStage);
@@ -621,9 +628,11 @@ static int sequence_step_pipelined(dvo_ctx* ctx, const uint8_t* frames, int n_ne
     CK(cudaEventRecord(ctx->evCall, st));
     CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCall, 0));
     if (ctx->pairsPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evPairsDone[L], 0));
+    const bool serial = prof_enabled();     // per-kernel timing pass: no overlap between stages, no side streams
+    if (serial && !fresh && ctx->pairsPending[L ^ 1]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evPairsDone[L ^ 1], 0));
     if (ctx->carryPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCarryCopied[L], 0));
     if ((rc = load_frames_into(ctx, ob, frames, n_new, pitch, frame_stride, slot0, kind, ctx->sOrb)) != 0) return rc;
-    launch_orb(ctx->og, ob, &tm, ctx->useTma, slot0, n_new, ctx->sOrb, &ctx->ss);
+    launch_orb(ctx->og, ob, &tm, ctx->useTma, slot0, n_new, ctx->sOrb, serial ? nullptr : &ctx->ss);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evOrbDone[L], ctx->sOrb));
     // ---- pair stage

@@ -25,6 +25,8 @@ constexpr int kFastBoxW = 160;       // TMA box: 16 + tile + 16 (multiple of 16 
 constexpr int kFastBoxH = 40;
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
+constexpr int kSelectSmallSmemBytes = 64 * 1024;     // k_select launch for the small pyramid levels (3 CTAs per SM)
+constexpr long long kSelectBigLevelPixels = 600000;  // levels above this go to the 160 KB launch (~0.1 B of list per pixel)
 constexpr int kSelectSmemBytes = 160 * 1024;   // k_select working array: 40960 candidates per level stay on chip
 constexpr int kMaxModels = 10;
 
@@ -125,8 +127,8 @@ struct ProfScope {
 // Side stream + events of a context: k_blur depends only on the pyramid, so it runs beside the latency-bound
 // compact -> select -> angle chain; host frames are staged through a double buffer on a copy stream.
 struct SideStreams {
-    cudaStream_t side = nullptr, copy = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr, copy = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr;
     cudaEvent_t evCopied[2] = {nullptr, nullptr}, evStageFree[2] = {nullptr, nullptr};
     bool stageUsed[2] = {false, false};
     uint8_t* stage[2] = {nullptr, nullptr};

@@ -31,9 +31,9 @@ __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
 
 // =========================================================================================== A.1 pyramid
 // Each thread owns 4 adjacent output columns (x coefficients and source offsets held in registers) and walks
-// kPyrRows output rows, so the per-pixel cost is 4 byte loads + the two fixed-point passes.
-constexpr int kPyrRows = 8;
-__global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0) {
+// `rows` output rows (8 on the large levels, 2 on the small ones where the grid would otherwise not fill the machine), so
+// the per-pixel cost is 4 byte loads + the two fixed-point passes.
+__global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0, int rows) {
     const LevelGeom& d = g.lv[L];
     const LevelGeom& s = g.lv[L - 1];
     const int slot = slot0 + blockIdx.z;
@@ -51,9 +51,9 @@ __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L
         cx1[k] = ex & 0xFFFF;
         ox1[k] = min(ox[k] + 1, s.w - 1);
     }
-    const int yBase = blockIdx.y * (8 * kPyrRows) + threadIdx.y;
+    const int yBase = blockIdx.y * (8 * rows) + threadIdx.y;
 #pragma unroll 2
-    for (int r = 0; r < kPyrRows; ++r) {
+    for (int r = 0; r < rows; ++r) {
         const int y = yBase + 8 * r;
         if (y >= d.h) break;
         const uint32_t ey = __ldg(ty + y);
@@ -575,10 +575,10 @@ struct BlockAcc {
 constexpr int kSelectThreads = 1024;
 constexpr int kSelectSeqTail = 64;    // ranges this short are finished by one warp running the scalar replay
 
-__global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes) {
+__global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes, int level0) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ SelShared sh;
-    const int L = blockIdx.y;                 // level-0 CTAs (the long ones) are dispatched first
+    const int L = level0 + blockIdx.y;        // the largest level of the launch (the long CTAs) is dispatched first
     const int slot = slot0 + blockIdx.x;
     const LevelGeom lv = g.lv[L];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
     // ---- pass 1: retainBest(2 * quota) on the FAST score, order-exact
     const bool inSmem1 = (size_t)n * sizeof(uint32_t) <= (size_t)smemBytes;
     uint32_t* work1 = inSmem1 ? reinterpret_cast<uint32_t*>(s_dyn) : b.selWork + (size_t)slot * g.candPerSlot + lv.candBase;
-    for (int i = tid; i < n; i += kSelectThreads) work1[i] = cand[i];
+    for (int i = tid; i < n; i += blockDim.x) work1[i] = cand[i];
     __syncthreads();
     int n1;
     {
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
 
     // ---- Harris response of the survivors (un-blurred level)
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
-    for (int i = warp; i < n1; i += kSelectThreads / 32) {
+    for (int i = warp; i < n1; i += blockDim.x >> 5) {
         uint32_t c = work1[i];
         int x = c & 0xFFF, y = (c >> 12) & 0xFFF;
         int sb, sc_;
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
     const bool inSmem2 = (size_t)n1 * sizeof(unsigned long long) <= (size_t)smemBytes;
     unsigned long long* work2 = inSmem2 ? reinterpret_cast<unsigned long long*>(s_dyn) : pairs;
     if (inSmem2) {
-        for (int i = tid; i < n1; i += kSelectThreads) work2[i] = pairs[i];
+        for (int i = tid; i < n1; i += blockDim.x) work2[i] = pairs[i];
     }
     __syncthreads();
     int n2;
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
     if (n2 > lv.finCap) { n2 = lv.finCap; flags |= 1; }
     uint32_t* finXY = b.finXY + (size_t)slot * g.finPerSlot + lv.finBase;
     float* finResp = b.finResp + (size_t)slot * g.finPerSlot + lv.finBase;
-    for (int i = tid; i < n2; i += kSelectThreads) {
+    for (int i = tid; i < n2; i += blockDim.x) {
         unsigned long long v = work2[i];
         finXY[i] = (uint32_t)(v & 0xFFFFFFu);
         finResp[i] = __uint_as_float((uint32_t)(v >> 32));
@@ -833,6 +833,7 @@ void prof_end(int id, cudaStream_t st) {
         if (g_profRecs[i].id == id) { cudaEventRecord(g_profRecs[i].b, st); return; }
 }
 void prof_enable(bool on) { g_profOn = on; }
+bool prof_enabled() { return g_profOn; }
 // total milliseconds and launch-group counts per id since the last collect (synchronises the device)
 void prof_collect(double* ms, int* count, int n) {
     cudaDeviceSynchronize();
@@ -888,9 +889,11 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     if (nSlots <= 0) return;
     cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
     for (int L = 1; L < g.nlevels; ++L) {
-        dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 8 * kPyrRows - 1) / (8 * kPyrRows), nSlots);
+        const long long ctas8 = (long long)((g.lv[L].w + 127) / 128) * ((g.lv[L].h + 63) / 64) * nSlots;
+        const int rows = ctas8 >= 148 * 16 ? 8 : 2;
+        dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 8 * rows - 1) / (8 * rows), nSlots);
         ProfScope ps_(PF_PYR, st);
-        k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0);
+        k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0, rows);
         ++g_launches;
         debug_sync("k_pyr_down", st);
     }
@@ -913,7 +916,25 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     { ProfScope ps_(PF_COMPACT, st); k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
     debug_sync("k_compact", st);
-    { ProfScope ps_(PF_SELECT, st); k_select<<<dim3(nSlots, g.nlevels), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes); }
+    {
+        // Large levels: 1024 threads and the whole 160 KB working array (one CTA per SM).  Small levels (candidate lists
+        // that fit 64 KB): 512 threads, three CTAs per SM, on a second side stream so both groups run together.
+        int nBig = 0;
+        while (nBig < g.nlevels && (long long)g.lv[nBig].w * g.lv[nBig].h > kSelectBigLevelPixels) ++nBig;
+        const bool split = fork && ss->side2 != nullptr && nBig > 0 && nBig < g.nlevels;
+        ProfScope ps_(PF_SELECT, st);
+        if (split) {
+            cudaEventRecord(ss->evFork2, st);
+            cudaStreamWaitEvent(ss->side2, ss->evFork2, 0);
+            k_select<<<dim3(nSlots, g.nlevels - nBig), 512, kSelectSmallSmemBytes, ss->side2>>>(g, b, slot0, kSelectSmallSmemBytes, nBig);
+            cudaEventRecord(ss->evJoin2, ss->side2);
+            k_select<<<dim3(nSlots, nBig), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes, 0);
+            cudaStreamWaitEvent(st, ss->evJoin2, 0);
+            ++g_launches;
+        } else {
+            k_select<<<dim3(nSlots, g.nlevels), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes, 0);
+        }
+    }
     ++g_launches;
     debug_sync("k_select", st);
     { ProfScope ps_(PF_ANGLE, st); k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
