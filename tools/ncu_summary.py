@@ -23,7 +23,7 @@ seen = {}
 for r in rows[2:]:
     name = r[idx[0][0]].split("(")[0]
     key = name + r[idx[1][0]]
-    if name in seen and seen[name] >= (7 if "pyr" in name else 1):
+    if name in seen and seen[name] >= (7 if "pyr" in name else (2 if "select" in name else 1)):
         continue
     seen[name] = seen.get(name, 0) + 1
     vals = []
