@@ -42,35 +42,65 @@ def parse():
     ap.add_argument("--ref-pairs-per-step", type=int, default=0, help="reference arm: pairs per step (0 = 2 x workers, min 8)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ingest", default="none", choices=["none", "grey", "bgr"],
+                    help="widened path (SURVEY 8f row 2): frames arrive distorted (grey or BGR) and cv.cvtColor + cv.undistort "
+                         "run inside the timed region on both arms; default: the BASELINE workload (undistorted mono frames)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "synthetic sequence %dx%d mono, ORB %d feats, 8 levels, crossCheck BF-Hamming, findEssentialMat RANSAC(0.999, 1px, 1000 it), recoverPose; consecutive-pair VO" % (
+    base = "synthetic sequence %dx%d mono, ORB %d feats, 8 levels, crossCheck BF-Hamming, findEssentialMat RANSAC(0.999, 1px, 1000 it), recoverPose; consecutive-pair VO" % (
         a.width, a.height, a.nfeatures)
+    if a.ingest != "none":
+        base += "; ingest: %s frames, cvtColor+undistort (reference calibration distortion) inside the timed region" % a.ingest
+    return base
+
+
+# distortion of /root/reference/Parameters/camera_calibration.yaml:25, used when --ingest is on
+INGEST_DIST = np.array([-0.296079, 0.099771, 0.000222, 0.000109, 0.0])
+
+
+def ingest_new_K(K):
+    """newCameraMatrix for the ingest runs: the focal lengths scaled like getOptimalNewCameraMatrix(alpha=1) does for this
+    distortion (0.81), principal point kept -- any matrix is valid input for cv.undistort / k_ingest."""
+    newK = np.array(K, dtype=np.float64).copy()
+    newK[0, 0] *= 0.81
+    newK[1, 1] *= 0.81
+    return newK
 
 
 # ================================================================================================ CPU reference (cv2)
-def _ref_worker_init(path, kpath, nf):
-    global _F, _K, _NF
+def _ref_worker_init(path, kpath, nf, ingest="none"):
+    global _F, _K, _NF, _ING
     import cv2
     cv2.setNumThreads(1)
     _F = np.load(path, mmap_mode="r")
     _K = np.load(kpath)
     _NF = nf
+    _ING = ingest
+
+
+def _ref_ingest(img):
+    import cv2
+    if _ING == "none":
+        return np.ascontiguousarray(img)
+    if _ING == "bgr":        # the reference decodes to BGR, converts, then undistorts (visual_odometry_v3.py:127-133)
+        img = cv2.cvtColor(np.ascontiguousarray(np.repeat(img[:, :, None], 3, axis=2)), cv2.COLOR_BGR2GRAY)
+    return cv2.undistort(np.ascontiguousarray(img), _K, INGEST_DIST, None, ingest_new_K(_K))
 
 
 def _ref_worker_pair(i):
     from oracle import cv2_chain
-    r = cv2_chain.frame_pair(np.ascontiguousarray(_F[i]), np.ascontiguousarray(_F[i + 1]), _K, _NF)   # both frames' ORB per pair,
-    return int(len(r["matches"]))                                                                    # as visual_odometry_v3.py:387-392
+    K = _K if _ING == "none" else ingest_new_K(_K)
+    r = cv2_chain.frame_pair(_ref_ingest(_F[i]), _ref_ingest(_F[i + 1]), K, _NF)     # both frames' ingest + ORB per pair,
+    return int(len(r["matches"]))                                                   # as visual_odometry_v3.py:387-392
 
 
 class CpuReference:
     """The reference's per-pair chain through cv2 (oracle/cv2_chain.py), one worker process per host core over
     independent pairs, cv2 internal threading off in each worker.  Falls back to the numpy port only if cv2 is absent."""
 
-    def __init__(self, frames_u8: np.ndarray, K: np.ndarray, nfeatures: int, workers: int | None = None):
+    def __init__(self, frames_u8: np.ndarray, K: np.ndarray, nfeatures: int, workers: int | None = None, ingest: str = "none"):
         import multiprocessing as mp
         from oracle import cv2_chain
         self.kind = "reference" if cv2_chain.available() else "port"
@@ -84,7 +114,7 @@ class CpuReference:
         self.path, self.kpath = os.path.join(self.tmp, "frames.npy"), os.path.join(self.tmp, "K.npy")
         np.save(self.path, frames_u8)
         np.save(self.kpath, np.asarray(K, dtype=np.float64))
-        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_ref_worker_init, initargs=(self.path, self.kpath, nfeatures))
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_ref_worker_init, initargs=(self.path, self.kpath, nfeatures, ingest))
         self.pool.map(_ref_worker_pair, [0] * self.workers)     # spin every worker up (imports, cv2 init)
 
     def run_pairs(self, idx):
@@ -130,7 +160,7 @@ def run_reference(a):
     pps = a.ref_pairs_per_step or max(8, 2 * workers)
     pps = min(pps, 256)
     frames, K = render_host_frames(pps + 1, a)
-    ref = CpuReference(frames, K, a.nfeatures, workers)
+    ref = CpuReference(frames, K, a.nfeatures, workers, a.ingest)
     for _ in range(max(a.warmup, 0)):
         ref.run_pairs(range(min(pps, workers)))
     t0 = time.perf_counter()
@@ -217,6 +247,12 @@ def run_b200(a):
     n_frames = (K_steps + W_steps) * B + 1
     frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * 5000)
     ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local)
+    Kpose = Kmat
+    if a.ingest != "none":
+        Kpose = ingest_new_K(Kmat)
+        ctx.set_undistort(Kmat, INGEST_DIST, Kpose, channels=3 if a.ingest == "bgr" else 1)
+        if a.ingest == "bgr":
+            frames = frames[:, :, :, None].expand(-1, -1, -1, 3).contiguous()
     rec = POSE_DTYPE.itemsize
     poses_dev = torch.zeros((K_steps + W_steps) * B * rec, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world * K_steps * B * rec, dtype=torch.uint8, device=dev) if world > 1 else None
@@ -234,7 +270,7 @@ def run_b200(a):
             lo = s * B + (0 if (fresh and s == first_step) else 1)
             hi = (s + 1) * B + 1
             out = poses_dev[pairs * rec + first_step * B * rec:]
-            pairs += ctx.sequence_step(frames[lo:hi], Kmat, out, first=(fresh and s == first_step))
+            pairs += ctx.sequence_step(frames[lo:hi], Kpose, out, first=(fresh and s == first_step))
         return pairs
 
     # ---- warm-up (also primes the carry slot so every timed step is B pairs)
@@ -275,7 +311,7 @@ def run_b200(a):
         pairs = 0
         for s in range(nsteps):
             lo = s * B + (0 if s == 0 else 1)
-            pairs += ctx.sequence_step(e2e_frames[lo:(s + 1) * B + 1], Kmat, poses_host[pairs:], first=(s == 0))
+            pairs += ctx.sequence_step(e2e_frames[lo:(s + 1) * B + 1], Kpose, poses_host[pairs:], first=(s == 0))
         ctx.sync()
         return pairs
     host_pass(min(2, K_steps))
@@ -301,7 +337,8 @@ def run_b200(a):
         px = level_pixel_counts(ctx)
         total_px = sum(px)
         pyr_bytes = sum(px[L - 1] + px[L] for L in range(1, len(px)))
-        alg_bytes_per_frame = {"k_pyr_down": pyr_bytes, "k_fast_nms": total_px, "k_blur": 2 * total_px}
+        alg_bytes_per_frame = {"k_pyr_down": pyr_bytes, "k_fast_nms": total_px, "k_blur": 2 * total_px,
+                               "k_ingest": px[0] * ((3 if a.ingest == "bgr" else 1) + 1)}
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         peaks = {}
         try:
@@ -354,8 +391,8 @@ def run_b200(a):
     if rank == 0 and not a.no_cpu_baseline:
         workers = os.cpu_count() or 1
         pps = min(max(8, 2 * workers), 128)
-        fr = frames[:pps + 1].cpu().numpy()
-        ref = CpuReference(fr, Kmat, a.nfeatures, workers)
+        fr = (frames[:pps + 1, :, :, 0] if a.ingest == "bgr" else frames[:pps + 1]).contiguous().cpu().numpy()
+        ref = CpuReference(fr, Kmat, a.nfeatures, workers, a.ingest)
         t0 = time.perf_counter()
         done = 0
         while True:
@@ -377,7 +414,8 @@ def run_b200(a):
                               B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
                           "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
                           "pairs_ok_fraction": ok_frac, "pair_stats": pair_stats},
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height, "d2h_bytes_per_step": B * rec},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height * (3 if a.ingest == "bgr" else 1),
+                       "d2h_bytes_per_step": B * rec},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -71,6 +71,7 @@ def load_library():
     lib.dvo_kernel_launches.argtypes = [vp]
     lib.dvo_kernel_launches.restype = ctypes.c_longlong
     lib.dvo_load_frames.argtypes = [vp, vp, ci, cs, cs, ci, ci, vp]
+    lib.dvo_set_undistort.argtypes = [vp, vp, vp, ci, vp, ci, vp]
     lib.dvo_orb.argtypes = [vp, ci, ci, vp]
     lib.dvo_get_features.argtypes = [vp, ci, ctypes.POINTER(dvo_features), vp]
     lib.dvo_pairs.argtypes = [vp, ci, ci, ci, vp, vp]
@@ -170,17 +171,40 @@ class Context:
         return w.value, h.value, q.value
 
     # ------------------------------------------------------------------ stages
+    def set_undistort(self, K=None, dist=None, new_K=None, channels=1):
+        """Ingest while loading: cv.cvtColor(BGR2GRAY) (channels=3) + cv.undistort(K, dist, new_K) on the GPU, bit-exact
+        with cv2.  channels=0 (or K=None) switches it off: frames are then grey and already undistorted."""
+        if K is None or channels == 0:
+            self._check(self.lib.dvo_set_undistort(self._h, None, None, 0, None, 0, self._stream()), "dvo_set_undistort")
+            self.channels = 1
+            return
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        Nc = np.ascontiguousarray(np.asarray(new_K, dtype=np.float64).reshape(9))
+        Dc = np.ascontiguousarray(np.asarray(dist if dist is not None else [], dtype=np.float64).ravel()[:8])
+        self._check(self.lib.dvo_set_undistort(self._h, Kc.ctypes.data, Dc.ctypes.data if Dc.size else None, int(Dc.size), Nc.ctypes.data,
+                                               int(channels), self._stream()), "dvo_set_undistort")
+        self.channels = int(channels)
+
+    def _frame_layout(self, frames):
+        """(row pitch, frame stride) in bytes of a contiguous (n, H, W[, 3]) uint8 batch, checked against the ingest mode."""
+        ch = getattr(self, "channels", 1)
+        want = (self.height, self.width) if ch == 1 else (self.height, self.width, 3)
+        assert tuple(frames.shape[1:]) == want, "frames must be (n, %s) uint8" % (", ".join(map(str, want)))
+        return self.width * ch, self.width * self.height * ch
+
     def load_frames(self, frames, slot0=0):
-        """frames: (n, H, W) uint8 torch tensor (cuda or cpu) or numpy array (host)."""
+        """frames: (n, H, W) uint8 -- or (n, H, W, 3) BGR after set_undistort(channels=3) -- torch tensor (cuda or cpu) or
+        numpy array (host)."""
         t = self.torch
         if isinstance(frames, np.ndarray):
             frames = t.from_numpy(np.ascontiguousarray(frames))
-        if frames.dim() == 2:
+        if frames.dim() == (2 if getattr(self, "channels", 1) == 1 else 3):
             frames = frames[None]
-        assert frames.dtype == t.uint8 and frames.shape[1] == self.height and frames.shape[2] == self.width
+        assert frames.dtype == t.uint8
         frames = frames.contiguous()
+        pitch, stride = self._frame_layout(frames)
         kind = 0 if frames.is_cuda else 1
-        self._check(self.lib.dvo_load_frames(self._h, frames.data_ptr(), frames.shape[0], self.width, self.width * self.height,
+        self._check(self.lib.dvo_load_frames(self._h, frames.data_ptr(), frames.shape[0], pitch, stride,
                                              slot0, kind, self._stream()), "dvo_load_frames")
         if kind == 1:
             self.sync()   # host source must outlive the copy
@@ -262,16 +286,17 @@ class Context:
             frames = t.from_numpy(np.ascontiguousarray(frames))
         frames = frames.contiguous()
         n = frames.shape[0]
+        pitch, stride = self._frame_layout(frames)
         Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
         if frames.is_cuda:
             dposes = t.empty((n - 1) * POSE_DTYPE.itemsize, dtype=t.uint8, device=self.tdev) if out is None else out
-            self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+            self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, pitch, stride, Kc.ctypes.data,
                                               dposes.data_ptr(), 0, self._stream()), "dvo_sequence")
             if out is not None:
                 return out
             return dposes.cpu().numpy().view(POSE_DTYPE)
         poses = np.zeros(n - 1, dtype=POSE_DTYPE)
-        self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+        self._check(self.lib.dvo_sequence(self._h, frames.data_ptr(), n, pitch, stride, Kc.ctypes.data,
                                           poses.ctypes.data, 1, self._stream()), "dvo_sequence")
         return poses
 
@@ -280,11 +305,12 @@ class Context:
         host tensor with poses_out a POSE_DTYPE ndarray.  Returns the number of records written."""
         Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
         n = frames.shape[0]
+        pitch, stride = self._frame_layout(frames)
         if frames.is_cuda:
-            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, pitch, stride, Kc.ctypes.data,
                                             poses_out.data_ptr(), 0, int(bool(first)), self._stream())
         else:
-            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, self.width, self.width * self.height, Kc.ctypes.data,
+            rc = self.lib.dvo_sequence_step(self._h, frames.data_ptr(), n, pitch, stride, Kc.ctypes.data,
                                             poses_out.ctypes.data, 1, int(bool(first)), self._stream())
         if rc < 0:
             self._check(rc, "dvo_sequence_step")

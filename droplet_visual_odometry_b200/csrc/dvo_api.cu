@@ -37,6 +37,8 @@ struct dvo_ctx {
     long long launchBase = 0;
     int carrySlot = -1;                // slot holding the last frame of the previous dvo_sequence_step
     SideStreams ss;
+    size_t stageBytes[2] = {0, 0};
+    IngestBuffers ingest;              // undistort map + weights; channels == 0: frames arrive grey and undistorted
     // Two-lane sequence pipeline (cfg.pipeline): lane 1 is a second set of ORB buffers so that the ORB stage of batch
     // s+1 (stream sOrb) runs while the pair stage of batch s (stream sPair) still reads batch s's features.
     OrbBuffers ob1{};
@@ -390,7 +392,7 @@ static int load_frames_into(dvo_ctx* ctx, const OrbBuffers& ob, const uint8_t* f
 
 int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, size_t frame_stride, int slot0, int kind,
                     void* stream) {
-    if (!ctx || !frames || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots || pitch < (size_t)ctx->cfg.width) {
+    if (!ctx || !frames || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots) {
         if (ctx) ctx->err = "dvo_load_frames: bad arguments";
         return DVO_E_INVALID;
     }
@@ -401,39 +403,111 @@ static int load_frames_into(dvo_ctx* ctx, const OrbBuffers& ob, const uint8_t* f
                             int slot0, int kind, cudaStream_t st) {
     const LevelGeom& l0 = ctx->og.lv[0];
     if (n == 0) return DVO_OK;
+    const int ch = ctx->ingest.channels > 0 ? ctx->ingest.channels : 1;
+    const size_t rowBytes = (size_t)l0.w * ch, frameBytes = rowBytes * l0.h;
+    if (pitch < rowBytes) { ctx->err = "dvo_load_frames: pitch smaller than width * channels"; return DVO_E_INVALID; }
+    auto to_slots = [&](const uint8_t* d_src, size_t p, size_t fs) {
+        if (ctx->ingest.channels > 0) launch_ingest(ctx->og, ob, ctx->ingest, d_src, n, p, fs, slot0, st);
+        else launch_load_frames(ctx->og, ob, d_src, n, p, fs, slot0, st);
+    };
     if (kind == 0) {
-        launch_load_frames(ctx->og, ob, frames, n, pitch, frame_stride, slot0, st);
+        to_slots(frames, pitch, frame_stride);
         CK(cudaGetLastError());
         return DVO_OK;
     }
     SideStreams& ss = ctx->ss;
-    if (ss.copy == nullptr) {   // side streams disabled: plain in-order copies
-        for (int i = 0; i < n; ++i) {
-            CK(cudaMemcpy2DAsync(ob.pyr + (size_t)(slot0 + i) * ctx->og.slotStride + l0.off, l0.pitch,
-                                 frames + (size_t)i * frame_stride, pitch, l0.w, l0.h, cudaMemcpyHostToDevice, st));
-        }
-        return DVO_OK;
-    }
-    // Host frames: H2D on the copy stream into one of two staging buffers (so the upload of the next batch overlaps the
-    // kernels of this one), then one kernel on the compute stream moves them into the slots.
-    const size_t frameBytes = (size_t)l0.w * l0.h;
+    // Host frames: H2D (on the copy stream when there is one, so the upload of the next batch overlaps the kernels of this
+    // one) into one of two staging buffers, then one kernel on the compute stream moves / ingests them into the slots.
     const int bsel = ss.stageIdx;
     ss.stageIdx ^= 1;
-    if (ss.stage[bsel] == nullptr) CK(cudaMalloc(&ss.stage[bsel], frameBytes * ctx->nSlots));
-    if (ss.stageUsed[bsel]) CK(cudaStreamWaitEvent(ss.copy, ss.evStageFree[bsel], 0));
-    if (pitch == (size_t)l0.w && frame_stride == frameBytes) {
-        CK(cudaMemcpyAsync(ss.stage[bsel], frames, frameBytes * n, cudaMemcpyHostToDevice, ss.copy));
+    const size_t need = frameBytes * ctx->nSlots;
+    if (ctx->stageBytes[bsel] < need) {
+        if (ss.stage[bsel]) { CK(cudaDeviceSynchronize()); CK(cudaFree(ss.stage[bsel])); ss.stage[bsel] = nullptr; }
+        CK(cudaMalloc(&ss.stage[bsel], need));
+        ctx->stageBytes[bsel] = need;
+    }
+    cudaStream_t cs = ss.copy != nullptr ? ss.copy : st;
+    if (ss.copy != nullptr && ss.stageUsed[bsel]) CK(cudaStreamWaitEvent(ss.copy, ss.evStageFree[bsel], 0));
+    if (pitch == rowBytes && frame_stride == frameBytes) {
+        CK(cudaMemcpyAsync(ss.stage[bsel], frames, frameBytes * n, cudaMemcpyHostToDevice, cs));
     } else {
         for (int i = 0; i < n; ++i)
-            CK(cudaMemcpy2DAsync(ss.stage[bsel] + (size_t)i * frameBytes, l0.w, frames + (size_t)i * frame_stride, pitch, l0.w, l0.h,
-                                 cudaMemcpyHostToDevice, ss.copy));
+            CK(cudaMemcpy2DAsync(ss.stage[bsel] + (size_t)i * frameBytes, rowBytes, frames + (size_t)i * frame_stride, pitch, rowBytes,
+                                 l0.h, cudaMemcpyHostToDevice, cs));
     }
-    CK(cudaEventRecord(ss.evCopied[bsel], ss.copy));
-    CK(cudaStreamWaitEvent(st, ss.evCopied[bsel], 0));
-    launch_load_frames(ctx->og, ob, ss.stage[bsel], n, l0.w, frameBytes, slot0, st);
-    CK(cudaEventRecord(ss.evStageFree[bsel], st));
-    ss.stageUsed[bsel] = true;
+    if (ss.copy != nullptr) {
+        CK(cudaEventRecord(ss.evCopied[bsel], ss.copy));
+        CK(cudaStreamWaitEvent(st, ss.evCopied[bsel], 0));
+    }
+    to_slots(ss.stage[bsel], rowBytes, frameBytes);
+    if (ss.copy != nullptr) {
+        CK(cudaEventRecord(ss.evStageFree[bsel], st));
+        ss.stageUsed[bsel] = true;
+    }
     CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+// Grey conversion + undistortion while loading (replaces cv.cvtColor + cv.undistort of visual_odometry_v3.py:110-135).
+int dvo_set_undistort(dvo_ctx* ctx, const double* K, const double* dist, int n_dist, const double* newK, int channels, void* stream) {
+    if (!ctx) return DVO_E_INVALID;
+    if (channels == 0) { ctx->ingest.channels = 0; return DVO_OK; }
+    if (!K || !newK || (n_dist > 0 && !dist) || n_dist < 0 || (channels != 1 && channels != 3)) {
+        ctx->err = "dvo_set_undistort: bad arguments (channels must be 0, 1 or 3)";
+        return DVO_E_INVALID;
+    }
+    IngestParams prm{};
+    {   // inv(newK) by cofactors, float64
+        const double* m = newK;
+        const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+        const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+        if (!(std::fabs(det) > 0)) { ctx->err = "dvo_set_undistort: newCameraMatrix is singular"; return DVO_E_INVALID; }
+        const double id = 1.0 / det;
+        prm.ir[0] = c00 * id; prm.ir[1] = (m[2] * m[7] - m[1] * m[8]) * id; prm.ir[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+        prm.ir[3] = c01 * id; prm.ir[4] = (m[0] * m[8] - m[2] * m[6]) * id; prm.ir[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+        prm.ir[6] = c02 * id; prm.ir[7] = (m[1] * m[6] - m[0] * m[7]) * id; prm.ir[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    }
+    prm.fx = K[0]; prm.fy = K[4]; prm.cx = K[2]; prm.cy = K[5];
+    for (int i = 0; i < 8; ++i) prm.k[i] = i < n_dist ? dist[i] : 0.0;
+    int rc;
+    if (ctx->ingest.map == nullptr) {
+        uint2* wt = nullptr;
+        if ((rc = dalloc(ctx, &ctx->ingest.map, (size_t)ctx->og.lv[0].w * ctx->og.lv[0].h)) != 0) return rc;
+        if ((rc = dalloc(ctx, &wt, 1024)) != 0) return rc;
+        // cv2's BilinearTab_i: float32 products of (1 - a | a), rounded to 1/32768, largest/smallest patched to sum 32768
+        std::vector<uint2> tab(1024);
+        const float s = 1.0f / 32;
+        for (int fy = 0; fy < 32; ++fy)
+            for (int fx = 0; fx < 32; ++fx) {
+                volatile float ay = fy * s, ax = fx * s;
+                volatile float cy[2] = {1.0f - ay, ay}, cx[2] = {1.0f - ax, ax};
+                int it[4], sum = 0;
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        volatile float v = cy[a] * cx[b];
+                        volatile float sc = v * 32768.0f;
+                        it[a * 2 + b] = (int)std::lrintf(sc);
+                        sum += it[a * 2 + b];
+                    }
+                const int diff = sum - 32768;
+                if (diff != 0) {
+                    int mk = 0, Mk = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        if (it[k] < it[mk]) mk = k;
+                        else if (it[k] > it[Mk]) Mk = k;
+                    }
+                    if (diff < 0) it[Mk] -= diff; else it[mk] -= diff;
+                }
+                tab[fy * 32 + fx] = make_uint2((uint32_t)(uint16_t)it[0] | ((uint32_t)(uint16_t)it[1] << 16),
+                                               (uint32_t)(uint16_t)it[2] | ((uint32_t)(uint16_t)it[3] << 16));   // 0 .. 32768
+            }
+        CK(cudaMemcpy(wt, tab.data(), sizeof(uint2) * 1024, cudaMemcpyHostToDevice));
+        ctx->ingest.wtab = wt;
+    }
+    launch_build_undistort_map(ctx->og, ctx->ingest, prm, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize((cudaStream_t)stream));    // the map may be used from internal streams next
+    ctx->ingest.channels = channels;
     return DVO_OK;
 }
 
@@ -736,7 +810,7 @@ int dvo_profile_collect(double* ms, int* count, int n) {
 }
 const char* dvo_profile_name(int id) {
     static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_compact", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
-                                          "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final"};
+                                          "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final", "k_ingest"};
     return (id >= 0 && id < PF_COUNT) ? names[id] : "";
 }
 

@@ -113,9 +113,21 @@ struct PairBuffers {
     PoseScratch* poseScratch;   // [pairs]
 };
 
+// ---- image ingest (cv.cvtColor BGR2GRAY + cv.undistort; /root/reference/scripts/visual_odometry_v3.py:110-135)
+struct IngestParams {
+    double ir[9];            // inv(newCameraMatrix)
+    double fx, fy, cx, cy;   // cameraMatrix
+    double k[8];             // k1 k2 p1 p2 k3 k4 k5 k6
+};
+struct IngestBuffers {
+    uint2* map = nullptr;        // [h][w]: x = (u16)sx | (u16)sy << 16 (integer source position, int16), y = fy << 5 | fx
+    const uint2* wtab = nullptr; // [32*32]: four uint16 bilinear weights (taps 00 01 10 11), sum 32768
+    int channels = 0;            // 0 = ingest disabled (frames are already grey + undistorted); 1 grey, 3 BGR
+};
+
 // ---- per-kernel CUDA-event profiler (bench.py's roofline pass; off by default, zero cost when off)
 enum ProfId { PF_PYR = 0, PF_FAST, PF_COMPACT, PF_SELECT, PF_ANGLE, PF_BLUR, PF_BRIEF, PF_NN, PF_SORT, PF_RANSAC,
-              PF_CHEIRALITY, PF_POSE_FINAL, PF_COUNT };
+              PF_CHEIRALITY, PF_POSE_FINAL, PF_INGEST, PF_COUNT };
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
 struct ProfScope {
@@ -138,6 +150,9 @@ struct SideStreams {
 // ---- launchers (orb_kernels.cu / pair_kernels.cu) ---------------------------------------------------------------
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st, const SideStreams* ss);
+void launch_build_undistort_map(const OrbGeom& g, const IngestBuffers& ib, const IngestParams& prm, cudaStream_t st);
+void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& ib, const uint8_t* d_src, int n, size_t pitch,
+                   size_t frameStride, int slot0, cudaStream_t st);
 void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_src, int n, size_t pitch, size_t frameStride,
                         int slot0, cudaStream_t st);
 void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,

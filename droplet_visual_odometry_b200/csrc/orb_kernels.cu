@@ -884,6 +884,86 @@ void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_
     ++g_launches;
 }
 
+// =========================================================================================== image ingest
+// cv.undistort == remap(src, initUndistortRectifyMap(K, dist, I, newK, size, CV_16SC2), INTER_LINEAR, BORDER_CONSTANT 0):
+// the map (float64, rounded to 1/32 px) is built once per calibration; per frame one gather kernel does grey conversion
+// (3735 B + 19235 G + 9798 R, >> 15) of the four taps and the int16-weight bilinear blend, straight into pyramid level 0.
+// Restated and checked against cv2 in oracle/ingest_np.py.
+__global__ void __launch_bounds__(256) k_build_undistort_map(OrbGeom g, IngestBuffers ib, IngestParams p) {
+    const int w = g.lv[0].w, h = g.lv[0].h;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= w || i >= h) return;
+    const double di = (double)i, dj = (double)j;
+    const double X = dadd(dadd(dmul(di, p.ir[1]), p.ir[2]), dmul(dj, p.ir[0]));
+    const double Y = dadd(dadd(dmul(di, p.ir[4]), p.ir[5]), dmul(dj, p.ir[3]));
+    const double W = dadd(dadd(dmul(di, p.ir[7]), p.ir[8]), dmul(dj, p.ir[6]));
+    const double wv = 1.0 / W;
+    const double x = dmul(X, wv), y = dmul(Y, wv);
+    const double x2 = dmul(x, x), y2 = dmul(y, y), r2 = dadd(x2, y2), xy2 = dmul(dmul(2.0, x), y);
+    const double num = dadd(1.0, dmul(dadd(dmul(dadd(dmul(p.k[4], r2), p.k[1]), r2), p.k[0]), r2));
+    const double den = dadd(1.0, dmul(dadd(dmul(dadd(dmul(p.k[7], r2), p.k[6]), r2), p.k[5]), r2));
+    const double kr = num / den;
+    const double xd = dadd(dadd(dmul(x, kr), dmul(p.k[2], xy2)), dmul(p.k[3], dadd(r2, dmul(2.0, x2))));
+    const double yd = dadd(dadd(dmul(y, kr), dmul(p.k[2], dadd(r2, dmul(2.0, y2)))), dmul(p.k[3], xy2));
+    const double u = dadd(dmul(p.fx, xd), p.cx), v = dadd(dmul(p.fy, yd), p.cy);
+    const int iu = __double2int_rn(dmul(u, 32.0)), iv = __double2int_rn(dmul(v, 32.0));
+    const int sx = max(-32768, min(32767, iu >> 5)), sy = max(-32768, min(32767, iv >> 5));
+    ib.map[(size_t)i * w + j] = make_uint2((uint32_t)(uint16_t)(short)sx | ((uint32_t)(uint16_t)(short)sy << 16),
+                                           (uint32_t)(((iv & 31) << 5) | (iu & 31)));
+}
+
+template <int kChannels>
+__device__ __forceinline__ int ingest_tap(const uint8_t* frame, size_t pitch, int w, int h, int y, int x) {
+    if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return 0;      // BORDER_CONSTANT, value 0
+    const uint8_t* q = frame + (size_t)y * pitch + (size_t)x * kChannels;
+    if (kChannels == 1) return q[0];
+    return (3735 * (int)q[0] + 19235 * (int)q[1] + 9798 * (int)q[2] + (1 << 14)) >> 15;
+}
+
+template <int kChannels>
+__global__ void __launch_bounds__(256) k_ingest(OrbGeom g, OrbBuffers b, IngestBuffers ib, const uint8_t* __restrict__ src, size_t pitch,
+                                                size_t frameStride, int slot0) {
+    const LevelGeom& l0 = g.lv[0];
+    const int y = blockIdx.y, f = blockIdx.z;
+    const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x4 >= l0.w) return;
+    const uint8_t* frame = src + (size_t)f * frameStride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        if (x >= l0.w) break;
+        const uint2 m = __ldg(ib.map + (size_t)y * l0.w + x);
+        const int sx = (int)(short)(m.x & 0xFFFFu), sy = (int)(short)(m.x >> 16);
+        const uint2 wq = __ldg(ib.wtab + m.y);
+        const int w00 = (int)(wq.x & 0xFFFFu), w01 = (int)(wq.x >> 16);      // unsigned: the integer-position entry is 32768
+        const int w10 = (int)(wq.y & 0xFFFFu), w11 = (int)(wq.y >> 16);
+        const int acc = ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx) * w00 +
+                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx + 1) * w01 +
+                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx) * w10 +
+                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx + 1) * w11;
+        const int v = max(0, min(255, (acc + (1 << 14)) >> 15));
+        out |= (uint32_t)v << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(b.pyr + (size_t)(slot0 + f) * g.slotStride + l0.off + (size_t)y * l0.pitch + x4) = out;
+}
+
+void launch_build_undistort_map(const OrbGeom& g, const IngestBuffers& ib, const IngestParams& prm, cudaStream_t st) {
+    dim3 grid((g.lv[0].w + 255) / 256, g.lv[0].h);
+    k_build_undistort_map<<<grid, 256, 0, st>>>(g, ib, prm);
+    ++g_launches;
+}
+
+void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& ib, const uint8_t* d_src, int n, size_t pitch,
+                   size_t frameStride, int slot0, cudaStream_t st) {
+    if (n <= 0) return;
+    dim3 grid((g.lv[0].w + 1023) / 1024, g.lv[0].h, n);
+    ProfScope ps_(PF_INGEST, st);
+    if (ib.channels == 3) k_ingest<3><<<grid, 256, 0, st>>>(g, b, ib, d_src, pitch, frameStride, slot0);
+    else k_ingest<1><<<grid, 256, 0, st>>>(g, b, ib, d_src, pitch, frameStride, slot0);
+    ++g_launches;
+}
+
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st, const SideStreams* ss) {
     if (nSlots <= 0) return;

@@ -172,12 +172,23 @@ class VisualOdometry:
             self.distortion_coefficient_matrix = np.array(data["distortion_coefficients"]["data"]).reshape((1, 5))
             self.previous_projection_matrix = np.matmul(self.intrinsic_coefficient_matrix, np.hstack((np.eye(3), np.zeros((3, 1)))))
 
-    def undistort_image(self, distorted_image, new_camera_matrix):     # reference :110-113 (ingest, outside the hot path)
-        import cv2 as cv
-        return cv.undistort(src=distorted_image, cameraMatrix=self.intrinsic_coefficient_matrix,
-                            distCoeffs=self.distortion_coefficient_matrix, newCameraMatrix=new_camera_matrix)
+    def undistort_image(self, distorted_image, new_camera_matrix):     # reference :110-113
+        """cv.undistort(src, cameraMatrix, distCoeffs, newCameraMatrix) on the GPU (k_ingest), bit-exact with cv2; accepts the
+        grey image the reference passes, or a BGR image (then cv.cvtColor(BGR2GRAY) is applied first, as :132 does)."""
+        img = np.ascontiguousarray(distorted_image, dtype=np.uint8)
+        eng = self._engine_for(img.shape[0], img.shape[1])
+        c = eng.ctx
+        c.set_undistort(self.intrinsic_coefficient_matrix, np.asarray(self.distortion_coefficient_matrix, dtype=np.float64).ravel(),
+                        new_camera_matrix, channels=3 if img.ndim == 3 else 1)
+        try:
+            c.load_frames(img, 0)
+            out = c.tap_image(0, 0, 0)
+        finally:
+            c.set_undistort(None)
+        return out
 
-    def ros_img_msg_to_opencv_image(self, image_message, msg_type):    # reference :115-135 (ingest, outside the hot path)
+    def ros_img_msg_to_opencv_image(self, image_message, msg_type):    # reference :115-135
+        """decode on the host (cv.imdecode is entropy decoding, outside the hot path), grey + undistort on the GPU."""
         import cv2 as cv
         new_camera_matrix, _ = cv.getOptimalNewCameraMatrix(self.intrinsic_coefficient_matrix, self.distortion_coefficient_matrix,
                                                             (self.frame_width, self.frame_height), 1, (self.frame_width, self.frame_height))
@@ -187,7 +198,9 @@ class VisualOdometry:
             image_np = np.frombuffer(image_message.data, dtype=np.uint8).reshape((image_message.height, image_message.width, -1))
         else:
             raise ValueError("unknown msg_type " + str(msg_type))
-        return self.undistort_image(cv.cvtColor(src=image_np, code=cv.COLOR_BGR2GRAY), new_camera_matrix)
+        if image_np.ndim == 3 and image_np.shape[2] == 1:
+            image_np = image_np[:, :, 0]
+        return self.undistort_image(image_np, new_camera_matrix)
 
     # ------------------------------------------------------------------ hot path
     def compute_current_image_elements(self, input_image):     # reference :370-379

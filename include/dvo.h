@@ -113,6 +113,14 @@ long long dvo_kernel_launches(const dvo_ctx* ctx);   /* kernels launched by this
 int dvo_load_frames(dvo_ctx* ctx, const uint8_t* frames, int n, size_t pitch, size_t frame_stride, int slot0, int kind,
                     void* stream);
 
+/* Image ingest while loading: replaces cv.cvtColor(BGR2GRAY) + cv.undistort(grey, cameraMatrix, distCoeffs,
+ * newCameraMatrix) of ros_img_msg_to_opencv_image / undistort_image (visual_odometry_v3.py:110-135), bit-exact with cv2.
+ * K, newK: 3x3 row-major (host); dist: k1 k2 p1 p2 [k3 [k4 k5 k6]] (host, n_dist <= 8).  channels = 1: frames passed to
+ * dvo_load_frames / dvo_sequence* are distorted grey images; 3: distorted BGR (pitch counts bytes, >= 3 * width);
+ * 0: switch ingest off again (frames are grey and already undistorted -- the default).  Builds the undistortion map
+ * for the context's frame size; synchronises `stream`. */
+int dvo_set_undistort(dvo_ctx* ctx, const double* K, const double* dist, int n_dist, const double* newK, int channels, void* stream);
+
 /* ORB detect+describe on slots [slot0, slot0+n): replaces feature_detector.detectAndCompute
  * (visual_odometry_v3.py:373, called from compute_current_image_elements :370-379). */
 int dvo_orb(dvo_ctx* ctx, int slot0, int n, void* stream);

@@ -275,3 +275,73 @@ def test_config2_sequence_against_ground_truth(env):
         assert rot_err_deg(rec[i]["R"], ref["R"]) <= ROT_TOL_DEG and dir_err_deg(rec[i]["t"], ref["t"]) <= TDIR_TOL_DEG
         assert abs(int(rec[i]["n_inliers"]) - int((ref["ransac_mask"] > 0).sum())) <= max(2, 0.05 * len(ref["matches"]))
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- ingest (§8f row 2)
+REF_K = np.array([[1173.854081, 0, 747.788206], [0, 1170.565083, 574.700374], [0, 0, 1]])       # Parameters/camera_calibration.yaml:29
+REF_D = np.array([-0.296079, 0.099771, 0.000222, 0.000109, 0.0])                                 # :25
+
+
+def _ingest_reference(img, K, D, newK):
+    try:
+        import cv2
+        grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) if img.ndim == 3 else img
+        return cv2.undistort(grey, K, D, None, newK)
+    except ImportError:
+        from oracle import ingest_np
+        return ingest_np.ingest(img, K, D, newK)
+
+
+@pytest.mark.parametrize("size,K,D", [((1440, 1080), REF_K, REF_D),
+                                      ((640, 480), np.array([[612.0, 0, 322.5], [0, 611.2, 238.1], [0, 0, 1]]), np.array([0.11, -0.23, 0.001, -0.0007, 0.05])),
+                                      ((333, 257), np.array([[300.0, 0, 160.0], [0, 305.0, 130.0], [0, 0, 1]]), np.array([-0.35, 0.15, 0, 0, -0.03, 0.01, 0.002, 0.0005]))])
+def test_ingest_grey_and_undistort_bit_exact(env, size, K, D):
+    """k_ingest == cv.cvtColor(BGR2GRAY) + cv.undistort (visual_odometry_v3.py:110-135), BGR and grey, device and host source"""
+    w, h = size
+    from oracle import ingest_np
+    newK = K.copy()
+    newK[0, 0] *= 0.81; newK[1, 1] *= 0.8; newK[0, 2] += 5.3; newK[1, 2] -= 3.1        # any newCameraMatrix must work
+    try:
+        import cv2
+        newK, _ = cv2.getOptimalNewCameraMatrix(K, D, (w, h), 1, (w, h))
+    except ImportError:
+        pass
+    rng = np.random.default_rng(w)
+    bgr = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    bgr[1] = np.clip(np.cumsum(rng.integers(-3, 4, (h, w, 3)), axis=1) + 128, 0, 255).astype(np.uint8)      # smooth image
+    ctx = env.native.Context(w, h, nfeatures=100, max_frames=2)
+    ctx.set_undistort(K, D, newK, channels=3)
+    for src in (bgr, env.torch.from_numpy(bgr).cuda()):
+        ctx.load_frames(src, 0)
+        for i in range(2):
+            assert np.array_equal(ctx.tap_image(i, 0, 0), _ingest_reference(bgr[i], K, D, newK)), (size, i)
+    grey = np.stack([ingest_np.bgr_to_gray(b) for b in bgr])
+    ctx.set_undistort(K, D, newK, channels=1)
+    ctx.load_frames(grey, 0)
+    assert np.array_equal(ctx.tap_image(1, 0, 0), _ingest_reference(grey[1], K, D, newK))
+    ctx.set_undistort(None)
+    ctx.load_frames(grey, 0)
+    assert np.array_equal(ctx.tap_image(0, 0, 0), grey[0])
+    ctx.close()
+
+
+def test_sequence_with_ingest_equals_sequence_of_preprocessed_frames(env):
+    """distorted frames through dvo_sequence with ingest on == cv2-undistorted frames through dvo_sequence with ingest off"""
+    from oracle import ingest_np
+    n, w, h = 7, 640, 480
+    frames, _, K = env.synth.render_sequence(n, width=w, height=h, device="cuda", start_index=11)
+    fh = frames.cpu().numpy()
+    D = np.array([-0.21, 0.07, 0.0004, -0.0003, 0.0])
+    newK = K.copy(); newK[0, 0] *= 0.9; newK[1, 1] *= 0.9
+    pre = np.stack([_ingest_reference(f, K, D, newK) for f in fh])
+    ctx = env.native.Context(w, h, nfeatures=500, max_frames=4)
+    base = ctx.sequence(pre, newK)
+    ctx.set_undistort(K, D, newK, channels=1)
+    for src in (fh, frames):
+        got = ctx.sequence(src, newK)
+        assert got.tobytes() == base.tobytes()
+    ctx.close()
+    from droplet_visual_odometry_b200.visual_odometry_v3 import VisualOdometry
+    vo = VisualOdometry(camera_matrix=K, nfeatures=100)
+    vo.distortion_coefficient_matrix = D
+    assert np.array_equal(vo.undistort_image(fh[0], newK), pre[0])

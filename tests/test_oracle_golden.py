@@ -102,3 +102,24 @@ def test_live_cv2_whole_chain():
     # config-4 matcher composition
     assert np.array_equal(C.match_knn_ratio(rc["feats_prev"]["desc"], rc["feats_cur"]["desc"]),
                           P.sort_matches(P.ratio_and_reverse_check(rc["feats_prev"]["desc"], rc["feats_cur"]["desc"])))
+
+
+def test_ingest_restatement_equals_cv2_gray_and_undistort():
+    """oracle/ingest_np.py (what k_ingest is checked against on the GPU) == cv2.cvtColor + cv2.undistort, bit for bit, with
+    the reference's two calibrations (/root/reference/Parameters/*.yaml values) and random images"""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ingest_np as I
+    rng = np.random.default_rng(11)
+    cases = [((1440, 1080), [1173.854081, 0, 747.788206, 0, 1170.565083, 574.700374, 0, 0, 1], [-0.296079, 0.099771, 0.000222, 0.000109, 0.0]),
+             ((640, 480), [612.0, 0, 322.5, 0, 611.2, 238.1, 0, 0, 1], [0.11, -0.23, 0.001, -0.0007, 0.05]),
+             ((333, 257), [300.0, 0, 160.0, 0, 305.0, 130.0, 0, 0, 1], [-0.35, 0.15, 0.0, 0.0, -0.03, 0.01, 0.002, 0.0005])]
+    for (w, h), Kl, D in cases:
+        K = np.array(Kl, np.float64).reshape(3, 3)
+        D = np.array(D, np.float64)
+        newK, _ = cv2.getOptimalNewCameraMatrix(K, D, (w, h), 1, (w, h))
+        bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        grey = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(I.bgr_to_gray(bgr), grey)
+        ref = cv2.undistort(grey, K, D, None, newK)
+        assert np.array_equal(I.ingest(bgr, K, D, newK), ref), (w, h)
+        assert np.array_equal(I.ingest(grey, K, D, newK), ref)
