@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     __shared__ __align__(128) uint8_t raw[kFastBoxH * kFastBoxW];
     __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
     __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
-    __shared__ uint16_t list2[(kTileH + 2) * (kTileW + 2)];
-    __shared__ int s_n1, s_n2, s_warpTot[8];
+    constexpr int kList2Cap = (kTileH + 2) * (kTileW + 2);
+    __shared__ uint16_t list2[kList2Cap];
+    __shared__ int s_n1, s_n2, s_n2b, s_warpTot[8];
     __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
                 : "memory");
         }
         for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
-        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
         // all threads wait for the bytes to land (phase 0)
         asm volatile(
             "{\n"
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             *reinterpret_cast<uint32_t*>(raw + ry * kFastBoxW + rw * 4) = v;
         }
         for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
-        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
     }
     __syncthreads();
 
@@ -225,12 +226,20 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
             pol = fast_corner_polarity16(*c, pr, th);
         }
-        const bool corner = pol != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, corner);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_n2, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
+        // corners with a brighter arc (pol 1 or 3) fill list2 from the front, darker-only ones (pol 2) from the back, so that
+        // phase 3's warps are polarity-uniform and run one of the two score loops, not both
+        const bool front = (pol & 1) != 0, back = pol == 2;
+        const unsigned mf = __ballot_sync(0xffffffffu, front), mb = __ballot_sync(0xffffffffu, back);
+        int basef = 0, baseb = 0;
+        if (lane == 0) {
+            if (mf) basef = atomicAdd(&s_n2, __popc(mf));
+            if (mb) baseb = atomicAdd(&s_n2b, __popc(mb));
+        }
+        basef = __shfl_sync(0xffffffffu, basef, 0);
+        baseb = __shfl_sync(0xffffffffu, baseb, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (front) list2[basef + __popc(mf & lt)] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
+        if (back) list2[kList2Cap - 1 - (baseb + __popc(mb & lt))] = (uint16_t)(code | (pol << 13));
     }
     __syncthreads();
 
@@ -238,9 +247,10 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     uint8_t* outmap = reinterpret_cast<uint8_t*>(list1);        // [kTileH][kTileW], zero = no keypoint
     reinterpret_cast<uint4*>(outmap)[tid] = make_uint4(0, 0, 0, 0);
     if (tid < kTileH) s_rowcnt[tid] = 0;
-    const int n2 = s_n2;
+    const int n2f = s_n2, n2 = n2f + s_n2b;
     for (int i = tid; i < n2; i += 256) {
-        const int code = list2[i] & 0x1FFF, pol = list2[i] >> 13;
+        const int e = list2[i < n2f ? i : kList2Cap - 1 - (i - n2f)];
+        const int code = e & 0x1FFF, pol = e >> 13;
         const uint8_t* c = raw + code;
         int pr[16];
 #pragma unroll
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull
     const int border = 31;
     for (int i = tid; i < n2; i += 256) {
-        const int code = list2[i] & 0x1FFF;
+        const int code = list2[i < n2f ? i : kList2Cap - 1 - (i - n2f)] & 0x1FFF;
         const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
         const int cy = ry - 3, cx = rx - 15;                   // ring coordinates: tile pixel (cx-1, cy-1)
         const int x = x0 + cx - 1, y = y0 + cy - 1;
@@ -713,24 +723,10 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
     const int tid = threadIdx.x;
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
     uint8_t* out = b.blur + (size_t)slot * g.slotStride + lv.off;
-    // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6  (BORDER_REFLECT_101 on both axes)
-    for (int i = tid; i < (kTileH + 6) * (kTileW / 4); i += 256) {
-        const int ry = i / (kTileW / 4), xq = (i - ry * (kTileW / 4)) * 4;
-        const int gx = x0 + xq;
-        if (gx >= lv.w) continue;             // whole quad outside the level: never read by the column pass
-        const int gy = reflect101(y0 - 3 + ry, lv.h);
-        const uint8_t* rowp = img + (size_t)gy * lv.pitch;
-        float p[10];
-        if (gx >= 4 && gx + 7 < lv.w) {
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp + gx);
-            const uint32_t w0 = __ldg(wp - 1), w1 = __ldg(wp), w2 = __ldg(wp + 1);
-            p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
-            p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
-            p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) p[k] = (float)rowp[reflect101(gx - 3 + k, lv.w)];
-        }
+    // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6  (BORDER_REFLECT_101 on both axes).
+    // Interior quads (three aligned words cover the 10 taps) go first with uniform warps; the few quads that touch the
+    // left / right image border (at most three per row) are done afterwards by a handful of threads.
+    auto row_quad = [&](const float* p, int ry, int xq) {
         float4 o;
         float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
@@ -745,6 +741,32 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
             ov[k] = s;
         }
         *reinterpret_cast<float4*>(hrow + ry * kTileW + xq) = o;
+    };
+    for (int i = tid; i < (kTileH + 6) * (kTileW / 4); i += 256) {
+        const int ry = i / (kTileW / 4), xq = (i - ry * (kTileW / 4)) * 4;
+        const int gx = x0 + xq;
+        if (!(gx >= 4 && gx + 7 < lv.w)) continue;      // border quad (or outside the level): second loop / never read
+        const int gy = reflect101(y0 - 3 + ry, lv.h);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx);
+        const uint32_t w0 = __ldg(wp - 1), w1 = __ldg(wp), w2 = __ldg(wp + 1);
+        float p[10];
+        p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
+        p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
+        p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
+        row_quad(p, ry, xq);
+    }
+    for (int i = tid; i < (kTileH + 6) * 3; i += 256) {
+        const int ry = i / 3, c = i - ry * 3;
+        const int lastq = (lv.w - 1) & ~3;
+        const int gx = c == 0 ? 0 : (c == 1 ? lastq : lastq - 4);
+        if (gx < x0 || gx >= x0 + kTileW || gx < 0 || (c > 0 && gx == 0)) continue;
+        if (gx >= 4 && gx + 7 < lv.w) continue;         // an interior quad after all
+        const int gy = reflect101(y0 - 3 + ry, lv.h);
+        const uint8_t* rowp = img + (size_t)gy * lv.pitch;
+        float p[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) p[k] = (float)rowp[reflect101(gx - 3 + k, lv.w)];
+        row_quad(p, ry, gx - x0);
     }
     __syncthreads();
     // column pass, 4 pixels per thread
