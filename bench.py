@@ -448,6 +448,11 @@ if __name__ == "__main__":
             run_b200(args)
     finally:
         sys.stdout.flush()
+        try:                      # C stdio buffers too (NCCL's banner is an fprintf(stdout)): flush them into stderr now
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
         os.dup2(_real_stdout, 1)
         os.close(_real_stdout)
         for ln in _lines:
