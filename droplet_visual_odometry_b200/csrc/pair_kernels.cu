@@ -11,6 +11,8 @@
 #include "dvo_internal.cuh"
 #include "mathcore.cuh"
 #include "fivepoint_group.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace dvo {
 void debug_sync(const char* name, cudaStream_t st);
@@ -190,12 +192,25 @@ struct RansacShared {
     int samples[kRansacGroups][5];
     int modelCount[kRansacGroups];
     int modelGood[kRansacGroups][kMaxModels];
+    int partial[kRansacGroups][kMaxModels];      // cluster mode: this CTA's share of the inlier counts
     int maxGood, niters, done, it0, bestIter, bestModel, hasBest, cnt;
 };
 
+// kCluster: a thread-block cluster of up to 8 CTAs works on ONE pair (few pairs, many correspondences -- BASELINE configs[4]).
+// Every CTA runs the identical, deterministic control flow (RNG, solves, replay), so the loop state stays in lock-step
+// without communication; only the Sampson scoring is split -- each CTA scores a slice of the correspondences -- and the
+// per-model counts are summed across the cluster through distributed shared memory between two cluster barriers.
+template <bool kCluster>
 __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
     __shared__ RansacShared sh;
-    const int pair = pair0 + blockIdx.x;
+    namespace cg = cooperative_groups;
+    unsigned crank = 0, csize = 1;
+    if (kCluster) {
+        cg::cluster_group cluster = cg::this_cluster();
+        crank = cluster.block_rank();
+        csize = cluster.num_blocks();
+    }
+    const int pair = pair0 + (kCluster ? blockIdx.x / csize : blockIdx.x);
     int* rs = pb.ransacState + pair * 8;
     const int M = pb.matchCount[pair];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -244,16 +259,19 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuff
             }
             const int n = five_point_solve_group(x1, x2, sh.scratch[grp], &sh.models[grp][0][0], gmask);
             if (gl == 0) sh.modelCount[grp] = n;
-            if (gl < 5) pb.samples[((size_t)pair * pg.maxIters + it0 + grp) * 5 + gl] = sh.samples[grp][gl];
+            if (gl < 5 && crank == 0) pb.samples[((size_t)pair * pg.maxIters + it0 + grp) * 5 + gl] = sh.samples[grp][gl];
         }
         __syncthreads();
         // Scoring: matches live in registers (two per thread per sweep), the models are broadcast from shared memory,
         // so each correspondence is read once per chunk and the loop is bound by the FP64 pipe, not by load latency.
-        for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads) (&sh.modelGood[0][0])[i] = 0;
+        int (*acc)[kMaxModels] = kCluster ? sh.partial : sh.modelGood;
+        for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads) (&acc[0][0])[i] = 0;
         __syncthreads();
-        for (int base = 0; base < M; base += 2 * kRansacThreads) {
+        const int per = (M + (int)csize - 1) / (int)csize;
+        const int mBeg = min(M, (int)crank * per), mEnd = min(M, mBeg + per);
+        for (int base = mBeg; base < mEnd; base += 2 * kRansacThreads) {
             const int i0 = base + tid, i1 = base + kRansacThreads + tid;
-            const bool v0 = i0 < M, v1 = i1 < M;
+            const bool v0 = i0 < mEnd, v1 = i1 < mEnd;
             const double4 p0 = v0 ? np4[i0] : make_double4(0, 0, 0, 0);
             const double4 p1 = v1 ? np4[i1] : make_double4(0, 0, 0, 0);
             for (int h = 0; h < nIt; ++h) {
@@ -265,11 +283,22 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuff
                     int good = (v0 && sampson_inlier(E, p0.x, p0.y, p0.z, p0.w, t32, tlo, thi)) ? 1 : 0;
                     good += (v1 && sampson_inlier(E, p1.x, p1.y, p1.z, p1.w, t32, tlo, thi)) ? 1 : 0;
                     good = __reduce_add_sync(0xffffffffu, good);
-                    if (lane == 0 && good) atomicAdd(&sh.modelGood[h][k], good);
+                    if (lane == 0 && good) atomicAdd(&acc[h][k], good);
                 }
             }
         }
-        __syncthreads();
+        if (kCluster) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();                               // every CTA's partial counts are complete
+            for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads) {
+                int tot = 0;
+                for (unsigned r = 0; r < csize; ++r) tot += cluster.map_shared_rank(&sh.partial[0][0], r)[i];
+                (&sh.modelGood[0][0])[i] = tot;
+            }
+            cluster.sync();                               // nobody still reads a partial that the next chunk will reset
+        } else {
+            __syncthreads();
+        }
         if (tid == 0) {
             int maxGood = sh.maxGood, niters = sh.niters;
             int it = it0;
@@ -294,6 +323,7 @@ __global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuff
         __syncthreads();
     }
     // ---- final state, mask of the winning model, SVD(E) -> R1, R2, t  (first half of recoverPose)
+    if (kCluster && crank != 0) return;      // lock-step loop: the last cluster barrier is behind every CTA
     PoseScratch& sc = ps[pair];
     uint8_t* mask = pb.ransacMask + (size_t)pair * pg.maxkp;
     const int hasBest = sh.hasBest;
@@ -446,7 +476,29 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
     const double thr = pg.threshold / ((fx + fy) / 2.0);
     const float t32 = (float)(thr * thr);
     PoseScratch* ps = pb.poseScratch;
-    { ProfScope ps_(PF_RANSAC, st); k_ransac<<<nPairs, kRansacThreads, 0, st>>>(pg, pb, ps, pair0, t32); }
+    {
+        ProfScope ps_(PF_RANSAC, st);
+        // few pairs with many correspondences: a cluster of CTAs per pair shares the scoring (DSMEM count reduction)
+        int csize = 1;
+        if (pg.maxkp >= 4096 && getenv("DVO_NO_CLUSTER") == nullptr) {
+            while (csize < 8 && nPairs * csize * 2 <= 148) csize *= 2;
+        }
+        if (csize > 1) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(nPairs * csize);
+            cfg.blockDim = dim3(kRansacThreads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_ransac<true>, pg, pb, ps, pair0, t32);
+        } else {
+            k_ransac<false><<<nPairs, kRansacThreads, 0, st>>>(pg, pb, ps, pair0, t32);
+        }
+    }
     debug_sync("k_ransac", st);
     { ProfScope ps_(PF_CHEIRALITY, st); k_cheirality<<<dim3((pg.maxkp + 127) / 128, nPairs), 128, 0, st>>>(pg, pb, ps, pair0); }
     debug_sync("k_cheirality", st);
