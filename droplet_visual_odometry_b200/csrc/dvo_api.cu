@@ -102,6 +102,7 @@ static int alloc_orb_buffers(dvo_ctx* ctx, OrbBuffers& b) {
     DA(b.featAngle, S * g.maxkp);
     DA(b.featOctave, S * g.maxkp);
     DA(b.featXY, S * g.maxkp);
+    DA(b.featCS, S * g.maxkp * 2);
     DA(b.featDesc, S * g.maxkp * 32);
     DA(b.featCount, S);
 #undef DA

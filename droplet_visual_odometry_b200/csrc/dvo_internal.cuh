@@ -71,6 +71,7 @@ struct OrbBuffers {
     float* featAngle;        // [slots][maxkp]
     int* featOctave;         // [slots][maxkp]
     uint32_t* featXY;        // [slots][maxkp] packed level coords
+    float* featCS;           // [slots][maxkp][2] cos, sin of the keypoint angle (float32 roundings of the float64 values)
     uint8_t* featDesc;       // [slots][maxkp][32]
     int* featCount;          // [slots]
     const uint32_t* resizeTab;   // per level: x table then y table, packed ofs<<16 | c1

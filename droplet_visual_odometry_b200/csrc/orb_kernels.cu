@@ -797,11 +797,34 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
 }
 
 // =========================================================================================== A.7 rBRIEF
-__device__ const signed char d_brief_pattern[256][4] = {
+static const signed char h_brief_pattern[256][4] = {
 #include "brief_pattern.inc"
 };
+// Transposed for the warp: entry [j][lane] = pair (lane * 8 + j) packed x0 | y0 << 8 | x1 << 16 | y1 << 24, so the 32 lanes of
+// a warp read 128 contiguous bytes per pair index instead of 32 sectors.  Filled by orb_kernels_init().
+__device__ uint32_t d_brief_pattern_t[8 * 32];
 
+// cos / sin of every keypoint's angle, one THREAD per keypoint: cv2 steers the pattern with float32 cos/sin of the float32
+// angle; computing them in float64 and rounding reproduces those values, and doing it here rather than per warp in
+// k_brief keeps the FP64 pipe out of that kernel (32x fewer FP64 instructions).
+__global__ void __launch_bounds__(256) k_trig(OrbGeom g, OrbBuffers b, int slot0) {
+    const int slot = slot0 + blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= b.featCount[slot]) return;
+    const size_t o = (size_t)slot * g.maxkp + i;
+    const float ang = fmul(b.featAngle[o], (float)(3.14159265358979323846 / 180.0));
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    b.featCS[o * 2] = (float)cd;
+    b.featCS[o * 2 + 1] = (float)sd;
+}
+
+// Warp per keypoint.  The rotated pattern stays within 18 px of the centre (|(x,y)| <= sqrt(13^2+13^2)), so the warp first
+// copies the 37-row x 44..48-byte window of the smoothed level into shared memory with aligned 32-bit loads (two rows per
+// instruction) and then gathers its 512 samples from there: ~60 L1 sectors per keypoint instead of 512 scattered byte loads.
+constexpr int kBriefR = 18, kBriefRows = 2 * kBriefR + 1, kBriefWords = 12;
 __global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot0) {
+    __shared__ __align__(16) uint32_t s_patch[8][kBriefRows * kBriefWords];
     const int slot = slot0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.x * 8 + warp;
@@ -813,20 +836,41 @@ __global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot
     // cv2: centre = (cvRound(pt.x * (1/scale)), cvRound(pt.y * (1/scale))) on the blurred level
     const float px = b.featPt[o * 2], py = b.featPt[o * 2 + 1];
     const int cx = __float2int_rn(fmul(px, lv.invScale)), cy = __float2int_rn(fmul(py, lv.invScale));
-    const float ang = fmul(b.featAngle[o], (float)(3.14159265358979323846 / 180.0));
-    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
-    const uint8_t* center = b.blur + (size_t)slot * g.slotStride + lv.off + (size_t)cy * lv.pitch + cx;
+    const float ca = b.featCS[o * 2], sa = b.featCS[o * 2 + 1];
+    const uint8_t* img = b.blur + (size_t)slot * g.slotStride + lv.off;
+    // window: rows cy-18..cy+18, bytes from xa = (cx-18) & ~3 (aligned), 12 words wide (covers cx+18: xa+47 >= cx+18+... )
+    const int xa = (cx - kBriefR) & ~3;
+    uint32_t* patch = s_patch[warp];
+    const bool inside = xa >= 0 && xa + 4 * kBriefWords <= lv.pitch && cy - kBriefR >= 0 && cy + kBriefR < lv.h;
+    if (inside) {
+        const int sub = lane / kBriefWords, wi = lane - sub * kBriefWords;     // lanes 0..23: two rows x 12 words
+        for (int r = 0; r < kBriefRows; r += 2) {
+            const int rr = r + sub;
+            if (sub < 2 && rr < kBriefRows)
+                patch[rr * kBriefWords + wi] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(cy - kBriefR + rr) * lv.pitch + xa) + wi);
+        }
+    }
+    __syncwarp();
+    const uint8_t* pb8 = reinterpret_cast<const uint8_t*>(patch) + kBriefR * (4 * kBriefWords) + (cx - xa);
+    const uint8_t* center = img + (size_t)cy * lv.pitch + cx;
     unsigned byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const signed char* pt = d_brief_pattern[lane * 8 + j];
-        float x0f = (float)pt[0], y0f = (float)pt[1], x1f = (float)pt[2], y1f = (float)pt[3];
+        const uint32_t pq = __ldg(&d_brief_pattern_t[j * 32 + lane]);
+        const float x0f = (float)(signed char)(pq & 0xFF), y0f = (float)(signed char)((pq >> 8) & 0xFF);
+        const float x1f = (float)(signed char)((pq >> 16) & 0xFF), y1f = (float)(signed char)(pq >> 24);
         int ix0 = __float2int_rn(fsub(fmul(x0f, ca), fmul(y0f, sa)));
         int iy0 = __float2int_rn(fadd(fmul(x0f, sa), fmul(y0f, ca)));
         int ix1 = __float2int_rn(fsub(fmul(x1f, ca), fmul(y1f, sa)));
         int iy1 = __float2int_rn(fadd(fmul(x1f, sa), fmul(y1f, ca)));
-        int t0 = center[iy0 * lv.pitch + ix0];
-        int t1 = center[iy1 * lv.pitch + ix1];
+        int t0, t1;
+        if (inside) {
+            t0 = pb8[iy0 * (4 * kBriefWords) + ix0];
+            t1 = pb8[iy1 * (4 * kBriefWords) + ix1];
+        } else {                               // never for cv2-selected keypoints (31-px border); keeps odd inputs safe
+            t0 = center[iy0 * lv.pitch + ix0];
+            t1 = center[iy1 * lv.pitch + ix1];
+        }
         byte |= (unsigned)(t0 < t1) << j;
     }
     b.featDesc[o * 32 + lane] = (uint8_t)byte;
@@ -1039,8 +1083,12 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     }
     ++g_launches;
     debug_sync("k_select", st);
-    { ProfScope ps_(PF_ANGLE, st); k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0); }
-    ++g_launches;
+    {
+        ProfScope ps_(PF_ANGLE, st);
+        k_angle_pack<<<dim3((g.maxkp + 7) / 8, nSlots), 256, 0, st>>>(g, b, slot0);
+        k_trig<<<dim3((g.maxkp + 255) / 256, nSlots), 256, 0, st>>>(g, b, slot0);
+    }
+    g_launches += 2;
     debug_sync("k_angle_pack", st);
     if (fork) {
         cudaStreamWaitEvent(st, ss->evJoin, 0);
@@ -1056,6 +1104,14 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
 
 void orb_kernels_init() {
     cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectSmemBytes);
+    uint32_t t[8 * 32];
+    for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 8; ++j) {
+            const signed char* p = h_brief_pattern[lane * 8 + j];
+            t[j * 32 + lane] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
+                               ((uint32_t)(uint8_t)p[3] << 24);
+        }
+    cudaMemcpyToSymbol(d_brief_pattern_t, t, sizeof t);
 }
 
 }  // namespace dvo
