@@ -12,7 +12,13 @@ cols = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("launch__bloc
         ("launch__registers_per_thread", "regs"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
-        ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 %"), ("smsp__inst_executed.sum", "warp instr")]
+        ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 %"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe %"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma pipe %"),
+        ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 pipe %"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu pipe %"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu pipe %"),
+        ("smsp__inst_executed.sum", "warp instr")]
 idx = [(h.index(c), n) for c, n in cols if c in h]
 print("# ncu --set full --clock-control none: %s\n" % rep.split("/")[-1])
 print("Per-launch values of the first captured launch of each kernel (cold caches, serialised by the profiler: compare shares,")
