@@ -367,7 +367,9 @@ def run_b200(a):
             if name == "k_nn":
                 # every distance is computed once (row and column minima from the same popcounts): N*N*8 POPC32 per pair
                 st["gpopc_per_s"] = round(nkp * nkp * 8 * B * cnt / (tms * 1e-3) / 1e9, 1)
-                st["frac_of_popc_peak"] = round(st["gpopc_per_s"] * 1e9 / (148 * 16 * 1.965e9), 4)   # 16 POPC/clk/SM nominal
+                # algorithmic POPC32 rate (8 per distance) against the nominal XU pipe rate, 16 POPC/clk/SM; the kernel executes
+                # 6 POPC per distance (two carry-save adders), so this can exceed 1
+                st["frac_of_popc_peak"] = round(st["gpopc_per_s"] * 1e9 / (148 * 16 * 1.965e9), 4)
             stages[name] = st
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         dms, dcnt = prof[dom]
