@@ -277,6 +277,16 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
         CK(cudaMemcpy(ctx->d_resizeTab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         b.resizeTab = ctx->d_resizeTab;
     }
+    {   // tile -> (level, tileX, tileY) table for the tiled image kernels
+        std::vector<uint32_t> ti(g.tilesPerFrame);
+        for (int L = 0; L < g.nlevels; ++L)
+            for (int t = 0; t < g.lv[L].tilesX * g.lv[L].tilesY; ++t)
+                ti[g.lv[L].tileBase + t] = (uint32_t)L | ((uint32_t)(t % g.lv[L].tilesX) << 4) | ((uint32_t)(t / g.lv[L].tilesX) << 16);
+        uint32_t* d_ti = nullptr;
+        DA(d_ti, ti.size());
+        CK(cudaMemcpy(d_ti, ti.data(), ti.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        b.tileInfo = d_ti;
+    }
     // pair buffers
     PairGeom& pg = ctx->pg;
     PairBuffers& pb = ctx->pb;
@@ -691,6 +701,7 @@ static int sequence_step_pipelined(dvo_ctx* ctx, const uint8_t* frames, int n_ne
         if ((rc = alloc_orb_buffers(ctx, ctx->ob1)) != 0) return rc;
         (void)mark;
         ctx->ob1.resizeTab = ctx->ob.resizeTab;
+        ctx->ob1.tileInfo = ctx->ob.tileInfo;
         memcpy(ctx->ob1.resizeTabOff, ctx->ob.resizeTabOff, sizeof(ctx->ob.resizeTabOff));
         if (ctx->useTma && (rc = build_tensor_maps(ctx, ctx->ob1, ctx->tmaps1)) != 0) return rc;
         CK(cudaDeviceSynchronize());

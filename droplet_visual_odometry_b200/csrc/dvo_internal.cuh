@@ -75,6 +75,7 @@ struct OrbBuffers {
     uint8_t* featDesc;       // [slots][maxkp][32]
     int* featCount;          // [slots]
     const uint32_t* resizeTab;   // per level: x table then y table, packed ofs<<16 | c1
+    const uint32_t* tileInfo;    // [tilesPerFrame] level | tileX << 4 | tileY << 16 for the 128x32 image-kernel tiles
     int resizeTabOff[kMaxLevels][2];
 };
 

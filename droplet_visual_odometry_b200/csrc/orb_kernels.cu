@@ -88,12 +88,10 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
-    const int tile = blockIdx.x;
-    const int L = find_level_by_tile(g, tile);
+    const uint32_t ti = __ldg(b.tileInfo + blockIdx.x);
+    const int L = ti & 15;
     const LevelGeom lv = g.lv[L];
-    const int t = tile - lv.tileBase;
-    const int tx = t % lv.tilesX, ty = t / lv.tilesX;
-    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int x0 = (int)((ti >> 4) & 0xFFF) * kTileW, y0 = (int)(ti >> 16) * kTileH;
     const int slot = slot0 + blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -113,7 +111,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
                 "l"(reinterpret_cast<uint64_t>(&tm.pyr[L])), "r"(smem_u32(&bar)), "r"(x0 - kFastHaloL), "r"(y0 - 4), "r"(slot)
                 : "memory");
         }
-        for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+        for (int i = tid; i < (kTileH + 2) * 136 / 16; i += 256) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
         // all threads wait for the bytes to land (phase 0)
         asm volatile(
@@ -145,7 +143,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             }
             *reinterpret_cast<uint32_t*>(raw + ry * kFastBoxW + rw * 4) = v;
         }
-        for (int i = tid; i < (kTileH + 2) * 136 / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+        for (int i = tid; i < (kTileH + 2) * 136 / 16; i += 256) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
     }
     __syncthreads();
@@ -226,20 +224,12 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
             for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
             pol = fast_corner_polarity16(*c, pr, th);
         }
-        // corners with a brighter arc (pol 1 or 3) fill list2 from the front, darker-only ones (pol 2) from the back, so that
-        // phase 3's warps are polarity-uniform and run one of the two score loops, not both
-        const bool front = (pol & 1) != 0, back = pol == 2;
-        const unsigned mf = __ballot_sync(0xffffffffu, front), mb = __ballot_sync(0xffffffffu, back);
-        int basef = 0, baseb = 0;
-        if (lane == 0) {
-            if (mf) basef = atomicAdd(&s_n2, __popc(mf));
-            if (mb) baseb = atomicAdd(&s_n2b, __popc(mb));
-        }
-        basef = __shfl_sync(0xffffffffu, basef, 0);
-        baseb = __shfl_sync(0xffffffffu, baseb, 0);
-        const unsigned lt = (1u << lane) - 1u;
-        if (front) list2[basef + __popc(mf & lt)] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
-        if (back) list2[kList2Cap - 1 - (baseb + __popc(mb & lt))] = (uint16_t)(code | (pol << 13));
+        const bool corner = pol != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, corner);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n2, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
     }
     __syncthreads();
 
@@ -247,9 +237,9 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     uint8_t* outmap = reinterpret_cast<uint8_t*>(list1);        // [kTileH][kTileW], zero = no keypoint
     reinterpret_cast<uint4*>(outmap)[tid] = make_uint4(0, 0, 0, 0);
     if (tid < kTileH) s_rowcnt[tid] = 0;
-    const int n2f = s_n2, n2 = n2f + s_n2b;
+    const int n2 = s_n2;
     for (int i = tid; i < n2; i += 256) {
-        const int e = list2[i < n2f ? i : kList2Cap - 1 - (i - n2f)];
+        const int e = list2[i];
         const int code = e & 0x1FFF, pol = e >> 13;
         const uint8_t* c = raw + code;
         int pr[16];
@@ -263,7 +253,7 @@ __global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const
     // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull
     const int border = 31;
     for (int i = tid; i < n2; i += 256) {
-        const int code = list2[i < n2f ? i : kList2Cap - 1 - (i - n2f)] & 0x1FFF;
+        const int code = list2[i] & 0x1FFF;
         const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
         const int cy = ry - 3, cx = rx - 15;                   // ring coordinates: tile pixel (cx-1, cy-1)
         const int x = x0 + cx - 1, y = y0 + cy - 1;
@@ -714,11 +704,10 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
     __shared__ __align__(16) float hrow[(kTileH + 6) * kTileW];
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
-    const int tile = blockIdx.x;
-    const int L = find_level_by_tile(g, tile);
+    const uint32_t ti = __ldg(b.tileInfo + blockIdx.x);
+    const int L = ti & 15;
     const LevelGeom lv = g.lv[L];
-    const int t = tile - lv.tileBase;
-    const int x0 = (t % lv.tilesX) * kTileW, y0 = (t / lv.tilesX) * kTileH;
+    const int x0 = (int)((ti >> 4) & 0xFFF) * kTileW, y0 = (int)(ti >> 16) * kTileH;
     const int slot = slot0 + blockIdx.y;
     const int tid = threadIdx.x;
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
