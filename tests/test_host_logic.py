@@ -104,3 +104,25 @@ def test_run_sharded_single_process_is_identity():
     assert np.array_equal(out, poses)
     with pytest.raises(ValueError):
         S.run_sharded(10, lambda a, b: poses[:1])
+
+
+def test_dropin_shims_resolve_the_reference_module_names():
+    """`from visual_odometry_v3 import VisualOdometry` / `import pose_estimation_module as PEM` (the reference's own import
+    lines, trajectory_evaluation_dual_process.py:21,23) work with dropin/ on sys.path; no GPU needed to import."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        for name in ("visual_odometry_v3", "pose_estimation_module"):
+            sys.modules.pop(name, None)
+        vo3 = importlib.import_module("visual_odometry_v3")
+        pem = importlib.import_module("pose_estimation_module")
+        assert hasattr(vo3, "VisualOdometry") and callable(vo3.VisualOdometry.visual_odometry_calculations)
+        for fn in ("rotation_matrix_to_quaternion", "write_to_output_file", "get_velocity_between_timestamps", "clear_txt_file_contents"):
+            assert hasattr(pem, fn), fn
+    finally:
+        sys.path.pop(0)
+        for name in ("visual_odometry_v3", "pose_estimation_module"):
+            sys.modules.pop(name, None)
