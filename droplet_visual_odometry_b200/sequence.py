@@ -158,3 +158,79 @@ class SequenceRunner:
         def fn(first, last):
             return self.run(frames[first:last + 1])
         return fn
+
+
+# ------------------------------------------------------------------------------------------------ ROS-free input (§8f rank 4)
+class FrameFolder:
+    """Frames of an offline sequence from a folder of images (or .npy arrays), in name order -- the ROS-free stand-in for
+    the rosbag pairing of get_valid_message_stream.py:21-87 and for CollectImagePaths
+    (utilities_folder/traj_eval_unit_vis_odom.py:23-34).  Indexing with a slice decodes just those frames, so a rank only
+    touches its own block.  Decoding (cv.imread) is host work outside the hot path; ``color=True`` keeps BGR for the GPU
+    ingest (Context.set_undistort(channels=3))."""
+    EXT = (".png", ".jpg", ".jpeg", ".bmp", ".pgm", ".tif", ".tiff", ".npy")
+
+    def __init__(self, folder, color: bool = False):
+        self.folder = folder
+        self.color = color
+        self.paths = sorted(os.path.join(folder, f) for f in os.listdir(folder) if f.lower().endswith(self.EXT))
+        if not self.paths:
+            raise FileNotFoundError("no frames in " + folder)
+
+    def __len__(self):
+        return len(self.paths)
+
+    @property
+    def timestamps(self):
+        """The file stem as a float when it parses (frames saved as <stamp>.png), else the frame index."""
+        out = []
+        for i, p in enumerate(self.paths):
+            stem = os.path.splitext(os.path.basename(p))[0]
+            try:
+                out.append(float(stem))
+            except ValueError:
+                out.append(float(i))
+        return out
+
+    def _read(self, path):
+        if path.lower().endswith(".npy"):
+            a = np.load(path)
+        else:
+            import cv2
+            a = cv2.imread(path, cv2.IMREAD_COLOR if self.color else cv2.IMREAD_GRAYSCALE)
+            if a is None:
+                raise IOError("cannot decode " + path)
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        if not self.color and a.ndim == 3:
+            raise ValueError(path + ": colour frame in a grey sequence (pass color=True and use the GPU ingest)")
+        return a
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return np.stack([self._read(p) for p in self.paths[idx]])
+        return self._read(self.paths[idx])
+
+
+def extract_trajectory(frames, K, out_dir, timestamps=None, nfeatures=500, batch=32, device=0, world_size=1, rank=0, group=None,
+                       undistort=None, start=None):
+    """The VO half of the reference's offline driver (trajectory_evaluation_dual_process.py:170-290) without ROS:
+    consecutive-pair VO over ``frames`` (FrameFolder, ndarray or tensor, indexable by slice), sharded by frame pair when
+    world_size > 1, chained, and written as the stamped_traj_estimate_* files (rank 0).  ``undistort=(K_raw, dist, new_K)``
+    switches the GPU ingest on (frames are then distorted; K must be new_K).  Returns (records, paths or None)."""
+    n = len(frames)
+    first = frames[0]
+    h, w = first.shape[0], first.shape[1]
+    runner = SequenceRunner(w, h, K, nfeatures=nfeatures, batch=batch, device=device)
+    if undistort is not None:
+        runner.ctx.set_undistort(undistort[0], undistort[1], undistort[2], channels=3 if first.ndim == 3 else 1)
+    torch_dev = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        torch_dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else None
+    records = run_sharded(n, runner.block_fn(frames), world_size, rank, group, torch_dev)
+    paths = None
+    if rank == 0:
+        ts = list(timestamps) if timestamps is not None else (frames.timestamps if hasattr(frames, "timestamps") else [float(i) for i in range(n)])
+        paths = write_trajectory(out_dir, ts, records, start=start)
+    runner.ctx.close()
+    return records, paths

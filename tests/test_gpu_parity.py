@@ -345,3 +345,28 @@ def test_sequence_with_ingest_equals_sequence_of_preprocessed_frames(env):
     vo = VisualOdometry(camera_matrix=K, nfeatures=100)
     vo.distortion_coefficient_matrix = D
     assert np.array_equal(vo.undistort_image(fh[0], newK), pre[0])
+
+
+def test_extract_trajectory_from_a_frame_folder(env, tmp_path):
+    """ROS-free driver (SURVEY 8f ranks 1 + 4): folder of frames -> VO -> stamped_traj_estimate_* files whose rows are the
+    chained poses of the same records the per-pair API gives."""
+    from droplet_visual_odometry_b200 import sequence as S
+    n, w, h = 9, 640, 480
+    frames, _, K = env.synth.render_sequence(n, width=w, height=h, device="cuda", start_index=40)
+    fh = frames.cpu().numpy()
+    for i in range(n):
+        np.save(tmp_path / ("%010.3f.npy" % (100.0 + 0.5 * i)), fh[i])
+    folder = S.FrameFolder(str(tmp_path))
+    rec, paths = S.extract_trajectory(folder, K, str(tmp_path / "out"), nfeatures=500, batch=4)
+    base = env.native.Context(w, h, nfeatures=500, max_frames=n, pipeline=False).sequence(frames, K)
+    assert rec.tobytes() == base.tobytes()
+    rows = {k: np.loadtxt(p).reshape(-1, 8) for k, p in paths.items()}
+    assert rows["absolute"].shape[0] == n and rows["relative"].shape[0] == n - 1 and rows["velocity"].shape[0] == n - 1
+    assert np.allclose(rows["absolute"][:, 0], 100.0 + 0.5 * np.arange(n)) and np.allclose(rows["relative"][:, 0], rows["absolute"][1:, 0])
+    T = np.eye(4)
+    for i in range(n - 1):
+        T = T.dot(S.relative_transform(rec[i]["R"], rec[i]["t"]))
+        assert np.allclose(rows["absolute"][i + 1, 1:4], T[:3, 3], atol=1e-9)
+    assert np.allclose(np.linalg.norm(rows["absolute"][:, 4:8], axis=1), 1.0, atol=1e-9)      # unit quaternions
+    with open(paths["absolute"]) as f:
+        assert f.readline().endswith(" \n")      # the reference's trailing space (pose_estimation_module.py:80-86)

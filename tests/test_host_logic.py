@@ -126,3 +126,24 @@ def test_dropin_shims_resolve_the_reference_module_names():
         sys.path.pop(0)
         for name in ("visual_odometry_v3", "pose_estimation_module"):
             sys.modules.pop(name, None)
+
+
+def test_frame_folder_reads_in_name_order_and_by_slice(tmp_path):
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (5, 48, 64), dtype=np.uint8)
+    for i, stamp in enumerate((10.5, 2.25, 7.0, 30.0, 4.5)):
+        np.save(tmp_path / ("%012.6f.npy" % stamp), imgs[i])
+    ff = S.FrameFolder(str(tmp_path))
+    order = np.argsort([10.5, 2.25, 7.0, 30.0, 4.5])
+    assert len(ff) == 5 and ff.timestamps == sorted([10.5, 2.25, 7.0, 30.0, 4.5])
+    assert np.array_equal(ff[1:4], imgs[order[1:4]]) and np.array_equal(ff[0], imgs[order[0]])
+    try:
+        import cv2
+    except ImportError:
+        return
+    d2 = tmp_path / "png"
+    d2.mkdir()
+    for i in range(3):
+        cv2.imwrite(str(d2 / ("frame_%03d.png" % i)), imgs[i])
+    fp = S.FrameFolder(str(d2))
+    assert fp.timestamps == [0.0, 1.0, 2.0] and np.array_equal(fp[0:3], imgs[:3])
