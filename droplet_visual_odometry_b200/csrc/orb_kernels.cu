@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool kUseTma>
-__global__ void __launch_bounds__(256) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
+__global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
     __shared__ __align__(128) uint8_t raw[kFastBoxH * kFastBoxW];
     __shared__ __align__(16) uint8_t sc[(kTileH + 2) * 136];
     __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
