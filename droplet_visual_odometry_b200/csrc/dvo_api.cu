@@ -272,6 +272,12 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
             b.resizeTabOff[L][1] = (int)tab.size();
             resize_axis_table(g.lv[L].h, g.lv[L - 1].h, tab);
         }
+        // k_pyr_down assumes the taps of 4 adjacent output columns span at most 8 source bytes
+        for (int L = 1; L < g.nlevels; ++L)
+            for (int x = 0; x + 3 < g.lv[L].w; x += 4) {
+                const uint32_t* t = tab.data() + b.resizeTabOff[L][0];
+                if ((int)(t[x + 3] >> 16) - (int)(t[x] >> 16) > 6) { ctx->err = "pyramid ratio too large for k_pyr_down"; return DVO_E_INVALID; }
+            }
         tab.push_back(0);
         DA(ctx->d_resizeTab, tab.size());
         CK(cudaMemcpy(ctx->d_resizeTab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -30,45 +30,74 @@ __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
 }
 
 // =========================================================================================== A.1 pyramid
-// Each thread owns 4 adjacent output columns (x coefficients and source offsets held in registers) and walks
-// `rows` output rows (8 on the large levels, 2 on the small ones where the grid would otherwise not fill the machine), so
-// the per-pixel cost is 4 byte loads + the two fixed-point passes.
+// CTA = 128 output columns x (8 * rows) output rows.  The source window of the tile (<= 171 x 78 px at the 1.2 ratio) is first
+// copied into shared memory with coalesced 128-bit loads; the four taps of every output pixel are then shared-memory byte
+// loads with 32-bit addressing (tap +1 and the next row are immediate offsets), which costs a third of the instructions of
+// gathering bytes from global memory with 64-bit addresses.  Each thread owns 4 adjacent output columns (x coefficients in
+// registers) and walks `rows` output rows (8 on the large levels, 2 on the small ones so that the grid fills the machine).
+// Clamping at the right / bottom edge is implicit: the coefficient tables give weight 0 to the tap past the last pixel.
+constexpr int kPyrSrcW = 176, kPyrSrcH = 82;
 __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0, int rows) {
+    __shared__ __align__(16) uint8_t tile[kPyrSrcH * kPyrSrcW];
     const LevelGeom& d = g.lv[L];
     const LevelGeom& s = g.lv[L - 1];
     const int slot = slot0 + blockIdx.z;
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (x4 >= d.w) return;
     const uint32_t* tx = b.resizeTab + b.resizeTabOff[L][0];
     const uint32_t* ty = b.resizeTab + b.resizeTabOff[L][1];
     const uint8_t* src = b.pyr + (size_t)slot * g.slotStride + s.off;
     uint8_t* dst = b.pyr + (size_t)slot * g.slotStride + d.off;
-    int ox[4], ox1[4], cx1[4];
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * (8 * rows);
+    const int yLast = min(y0 + 8 * rows - 1, d.h - 1);
+    const int sx0 = (int)(__ldg(tx + x0) >> 16);
+    const int sy0 = (int)(__ldg(ty + y0) >> 16), sy1 = (int)(__ldg(ty + yLast) >> 16) + 1;
+    const int ax0 = sx0 & ~15;
+    // always the full 176-byte rows (compile-time divisor below); what lies beyond sx1 is never used, and reading it is
+    // safe: rows are pitch-padded and the buffers end with slack
+    constexpr int nVec = kPyrSrcW / 16;
+    const int nRow = min(sy1 - sy0 + 1, kPyrSrcH);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < nRow * nVec; i += 256) {
+        const int r = i / nVec, v = i - r * nVec;
+        // row s.h (one past the image) is allocated padding; it only ever meets a zero weight
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)min(sy0 + r, s.h) * s.pitch + ax0) + v);
+        *reinterpret_cast<uint4*>(tile + r * kPyrSrcW + v * 16) = q;
+    }
+    __syncthreads();
+    const int x4 = x0 + threadIdx.x * 4;
+    if (x4 >= d.w) return;
+    // The 4 columns' taps (ox, ox+1) lie within 8 bytes of ox[0] (ratio 1.2: ox[3] - ox[0] <= 4; checked on the host), so a
+    // row needs three aligned 32-bit words, two funnel shifts to bring byte ox[0] to position 0, and per column one PRMT
+    // (pick the two taps) + one DP2A (two 16-bit weights x two bytes): 3 shared loads per source row instead of 8.
+    uint32_t wgt[4], sel[4];
+    int ox0 = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t ex = __ldg(tx + min(x4 + k, d.w - 1));
-        ox[k] = ex >> 16;
-        cx1[k] = ex & 0xFFFF;
-        ox1[k] = min(ox[k] + 1, s.w - 1);
+        const int o = (int)(ex >> 16) - ax0;
+        if (k == 0) ox0 = o;
+        const uint32_t c1 = ex & 0xFFFF, rel = (uint32_t)(o - ox0);
+        wgt[k] = (256u - c1) | (c1 << 16);
+        sel[k] = rel | ((rel + 1u) << 4);
     }
-    const int yBase = blockIdx.y * (8 * rows) + threadIdx.y;
-#pragma unroll 2
+    const int wofs = ox0 & ~3;
+    const uint32_t sh = (uint32_t)(ox0 & 3) * 8u;
     for (int r = 0; r < rows; ++r) {
-        const int y = yBase + 8 * r;
+        const int y = y0 + threadIdx.y + 8 * r;
         if (y >= d.h) break;
         const uint32_t ey = __ldg(ty + y);
-        const int oy = ey >> 16, cy1 = ey & 0xFFFF, cy0 = 256 - cy1;
-        const int oy1 = min(oy + 1, s.h - 1);
-        const uint8_t* r0 = src + (size_t)oy * s.pitch;
-        const uint8_t* r1 = src + (size_t)oy1 * s.pitch;
+        const uint32_t cy1 = ey & 0xFFFF, cy0 = 256u - cy1;
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(tile + ((int)(ey >> 16) - sy0) * kPyrSrcW + wofs);
+        const uint32_t* p1 = p0 + kPyrSrcW / 4;
+        const uint32_t a0 = p0[0], a1 = p0[1], a2 = p0[2], b0 = p1[0], b1 = p1[1], b2 = p1[2];
+        const uint32_t alo = __funnelshift_r(a0, a1, sh), ahi = __funnelshift_r(a1, a2, sh);
+        const uint32_t blo = __funnelshift_r(b0, b1, sh), bhi = __funnelshift_r(b1, b2, sh);
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int cx0 = 256 - cx1[k];
-            const int h0 = cx0 * (int)__ldg(r0 + ox[k]) + cx1[k] * (int)__ldg(r0 + ox1[k]);
-            const int h1 = cx0 * (int)__ldg(r1 + ox[k]) + cx1[k] * (int)__ldg(r1 + ox1[k]);
-            const int v = (h0 * cy0 + h1 * cy1 + (1 << 15)) >> 16;
-            out |= (uint32_t)v << (8 * k);
+            const uint32_t h0 = __dp2a_lo(wgt[k], __byte_perm(alo, ahi, sel[k]), 0u);
+            const uint32_t h1 = __dp2a_lo(wgt[k], __byte_perm(blo, bhi, sel[k]), 0u);
+            const uint32_t v = (h0 * cy0 + h1 * cy1 + (1u << 15)) >> 16;
+            out |= v << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x4) = out;
     }
