@@ -363,13 +363,11 @@ __global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int sl
             uint4 v = make_uint4(0, 0, 0, 0);
             if (x < lv.pitch) v = *reinterpret_cast<const uint4*>(map + (size_t)y * lv.pitch + x);
             const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-            int c = 0;
+            uint32_t nzw[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                // bytes != 0 -> one bit each
-                const uint32_t nz = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
-                c += __popc(nz);
-            }
+            for (int q = 0; q < 4; ++q)      // bytes != 0 -> their top bit
+                nzw[q] = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
+            const int c = __popc((nzw[0] >> 7) | (nzw[1] >> 6) | (nzw[2] >> 5) | (nzw[3] >> 4));      // one POPC for 16 bytes
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -377,17 +375,16 @@ __global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int sl
                 if (lane >= o) incl += nn;
             }
             int pos = running + incl - c;
-            if (c) {
+            if (c) {      // survivors are sparse (a few per 16 pixels at most): walk the set bits only
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (wv[q] == 0) continue;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    uint32_t m = nzw[q];
+                    while (m) {
+                        const int k = (__ffs(m) - 1) >> 3;
                         const uint32_t sv = (wv[q] >> (8 * k)) & 0xFFu;
-                        if (sv) {
-                            if (pos < lv.candCap) cand[pos] = (sv << 24) | ((uint32_t)y << 12) | (uint32_t)(x + 4 * q + k);
-                            ++pos;
-                        }
+                        if (pos < lv.candCap) cand[pos] = (sv << 24) | ((uint32_t)y << 12) | (uint32_t)(x + 4 * q + k);
+                        ++pos;
+                        m &= m - 1;
                     }
                 }
             }
