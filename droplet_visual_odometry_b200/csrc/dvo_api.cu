@@ -344,7 +344,11 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     }
     if (cfg->pipeline != 0 && getenv("DVO_NO_PIPELINE") == nullptr) {
         CK(cudaStreamCreateWithFlags(&ctx->sOrb, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&ctx->sPair, cudaStreamNonBlocking));
+        {   // the pair stage is short and latency-bound: give its CTAs first pick of freed SM resources
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&ctx->sPair, cudaStreamNonBlocking, hi));
+        }
         CK(cudaEventCreateWithFlags(&ctx->evCall, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&ctx->evOrbDone[i], cudaEventDisableTiming));

@@ -212,7 +212,7 @@ struct RansacShared {
 // without communication; only the Sampson scoring is split -- each CTA scores a slice of the correspondences -- and the
 // per-model counts are summed across the cluster through distributed shared memory between two cluster barriers.
 template <bool kCluster>
-__global__ void __launch_bounds__(kRansacThreads) k_ransac(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
+__global__ void __launch_bounds__(kRansacThreads, 2) k_ransac(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
     __shared__ RansacShared sh;
     namespace cg = cooperative_groups;
     unsigned crank = 0, csize = 1;
