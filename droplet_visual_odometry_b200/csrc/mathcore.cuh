@@ -88,6 +88,21 @@ DVO_HD bool ring_has9(uint32_t m) {
 
 DVO_HD int imin(int a, int b) { return a < b ? a : b; }
 DVO_HD int imax(int a, int b) { return a > b ? a : b; }
+// three-input min / max: one VIMNMX3 on sm_90+ (DPX), two compares elsewhere
+DVO_HD int imin3(int a, int b, int c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    return __vimin3_s32(a, b, c);
+#else
+    return imin(imin(a, b), c);
+#endif
+}
+DVO_HD int imax3(int a, int b, int c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    return __vimax3_s32(a, b, c);
+#else
+    return imax(imax(a, b), c);
+#endif
+}
 
 // Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
 // Returns the passing polarities: bit 0 = a 9-arc with every d > t, bit 1 = a 9-arc with every d < -t (0 = not a corner).
@@ -126,21 +141,19 @@ DVO_HD int fast_corner_score16(int v, const int* p, int t, int pol = 3) {
     if (pol & 1)
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        int a = imin(imin(d[k + 1], d[k + 2]), d[k + 3]);
+        int a = imin3(d[k + 1], d[k + 2], d[k + 3]);
         if (a <= a0) continue;
-        a = imin(a, imin(imin(d[k + 4], d[k + 5]), imin(d[k + 6], imin(d[k + 7], d[k + 8]))));
-        a0 = imax(a0, imin(a, d[k]));
-        a0 = imax(a0, imin(a, d[k + 9]));
+        a = imin3(a, imin3(d[k + 4], d[k + 5], d[k + 6]), imin(d[k + 7], d[k + 8]));
+        a0 = imax3(a0, imin(a, d[k]), imin(a, d[k + 9]));
     }
     int b0 = -a0;
     if (pol & 2)
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        int b = imax(imax(d[k + 1], d[k + 2]), d[k + 3]);
+        int b = imax3(d[k + 1], d[k + 2], d[k + 3]);
         if (b >= b0) continue;
-        b = imax(b, imax(imax(d[k + 4], d[k + 5]), imax(d[k + 6], imax(d[k + 7], d[k + 8]))));
-        b0 = imin(b0, imax(b, d[k]));
-        b0 = imin(b0, imax(b, d[k + 9]));
+        b = imax3(b, imax3(d[k + 4], d[k + 5], d[k + 6]), imax(d[k + 7], d[k + 8]));
+        b0 = imin3(b0, imax(b, d[k]), imax(b, d[k + 9]));
     }
     return -b0 - 1;
 }

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
     constexpr int kList2Cap = (kTileH + 2) * (kTileW + 2);
     __shared__ uint16_t list2[kList2Cap];
-    __shared__ int s_n1, s_n2, s_n2b, s_warpTot[8];
+    __shared__ int s_n1, s_n2, s_warpTot[8];
     __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
                 : "memory");
         }
         for (int i = tid; i < (kTileH + 2) * 136 / 16; i += 256) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
         // all threads wait for the bytes to land (phase 0)
         asm volatile(
             "{\n"
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
             *reinterpret_cast<uint32_t*>(raw + ry * kFastBoxW + rw * 4) = v;
         }
         for (int i = tid; i < (kTileH + 2) * 136 / 16; i += 256) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_n2b = 0; }
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; }
     }
     __syncthreads();
 
