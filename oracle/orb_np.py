@@ -6,7 +6,7 @@ reference's per-frame call ``VisualOdometry.compute_current_image_elements``
 
 The arithmetic itself lives in OpenCV (third-party, not vendored by the reference, not pinned by it; pinned for
 this build to cv2 4.13.0 -- SURVEY.md §8c).  Every function below restates one stage of OpenCV's published ORB
-algorithm as verified bit-for-bit against cv2 4.13.0; ``tests/test_oracle_vs_cv2.py`` and
+algorithm as verified bit-for-bit against cv2 4.13.0; ``tests/test_oracle_golden.py`` and
 the fixtures under ``tests/golden`` (made by ``tests/golden/make_golden.py`` from cv2 itself) pin it.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import this module.

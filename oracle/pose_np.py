@@ -11,7 +11,7 @@ OpenCV (third-party, unpinned by the reference, pinned here to cv2 4.13.0) holds
 its published algorithm and its observable control flow: RNG stream, 5-point sampling
 with single-index redraw, Nister 5-point minimal solver, Sampson error cast to float32, strict '>' update, adaptive
 iteration count, SVD decomposition, linear triangulation and the '>=' cheirality cascade.  Pinned against cv2 itself by
-``tests/test_oracle_vs_cv2.py`` and the fixtures under ``tests/golden``.
+``tests/test_oracle_golden.py`` and the fixtures under ``tests/golden``.
 """
 from __future__ import annotations
 
