@@ -739,8 +739,8 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
     uint8_t* out = b.blur + (size_t)slot * g.slotStride + lv.off;
     // row pass: s = k0*p[-3]; s = fma(k_i, p_i, s), i = 1..6  (BORDER_REFLECT_101 on both axes).
-    // Interior quads (three aligned words cover the 10 taps) go first with uniform warps; the few quads that touch the
-    // left / right image border (at most three per row) are done afterwards by a handful of threads.
+    // Interior octets (four aligned words cover the 14 taps of 8 outputs) go first with uniform warps; the few quads
+    // that touch the left / right image border (at most six per row) are done afterwards by a handful of threads.
     auto row_quad = [&](const float* p, int ry, int xq) {
         float4 o;
         float* ov = reinterpret_cast<float*>(&o);
@@ -757,25 +757,29 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
         }
         *reinterpret_cast<float4*>(hrow + ry * kTileW + xq) = o;
     };
-    for (int i = tid; i < (kTileH + 6) * (kTileW / 4); i += 256) {
-        const int ry = i / (kTileW / 4), xq = (i - ry * (kTileW / 4)) * 4;
-        const int gx = x0 + xq;
-        if (!(gx >= 4 && gx + 7 < lv.w)) continue;      // border quad (or outside the level): second loop / never read
+    auto interior = [&](int gxo) { return gxo >= 4 && gxo + 11 < lv.w; };      // gxo: first column of an aligned octet
+    for (int i = tid; i < (kTileH + 6) * (kTileW / 8); i += 256) {
+        const int ry = i / (kTileW / 8), xo = (i - ry * (kTileW / 8)) * 8;
+        const int gx = x0 + xo;
+        if (!interior(gx)) continue;      // border octet (or outside the level): second loop / never read
         const int gy = reflect101(y0 - 3 + ry, lv.h);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx);
-        const uint32_t w0 = __ldg(wp - 1), w1 = __ldg(wp), w2 = __ldg(wp + 1);
-        float p[10];
+        const uint32_t w0 = __ldg(wp - 1), w1 = __ldg(wp), w2 = __ldg(wp + 1), w3 = __ldg(wp + 2);
+        float p[14];
         p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
         p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
-        p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
-        row_quad(p, ry, xq);
+        p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF); p[10] = (float)(w2 >> 24);
+        p[11] = (float)(w3 & 0xFF); p[12] = (float)((w3 >> 8) & 0xFF); p[13] = (float)((w3 >> 16) & 0xFF);
+        row_quad(p, ry, xo);
+        row_quad(p + 4, ry, xo + 4);
     }
-    for (int i = tid; i < (kTileH + 6) * 3; i += 256) {
-        const int ry = i / 3, c = i - ry * 3;
-        const int lastq = (lv.w - 1) & ~3;
-        const int gx = c == 0 ? 0 : (c == 1 ? lastq : lastq - 4);
-        if (gx < x0 || gx >= x0 + kTileW || gx < 0 || (c > 0 && gx == 0)) continue;
-        if (gx >= 4 && gx + 7 < lv.w) continue;         // an interior quad after all
+    for (int i = tid; i < (kTileH + 6) * 6; i += 256) {
+        const int ry = i / 6, c = i - ry * 6;
+        const int lasto = (lv.w - 1) & ~7;
+        const int go = (c >> 1) == 0 ? 0 : ((c >> 1) == 1 ? lasto : lasto - 8);      // candidate border octets
+        const int gx = go + 4 * (c & 1);
+        if (go < 0 || ((c >> 1) > 0 && go == 0) || gx < x0 || gx >= x0 + kTileW || gx >= lv.w) continue;
+        if (interior(go)) continue;                     // an interior octet after all
         const int gy = reflect101(y0 - 3 + ry, lv.h);
         const uint8_t* rowp = img + (size_t)gy * lv.pitch;
         float p[10];
@@ -801,9 +805,8 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
             s = ffma(k2, fadd(d1.F, u1.F), s);                     \
             s = ffma(k1, fadd(d2.F, u2.F), s);                     \
             s = ffma(k0, fadd(d3.F, u3.F), s);                     \
-            int v = __float2int_rn(s);                             \
-            v = max(0, min(255, v));                               \
-            word |= (uint32_t)v << SH;                             \
+            /* 0 <= s <= 255 * (sum of weights)^2 < 255.5: no saturation needed */ \
+            word |= (uint32_t)__float2int_rn(s) << SH;             \
         }
         DVO_BLUR_COL(x, 0) DVO_BLUR_COL(y, 8) DVO_BLUR_COL(z, 16) DVO_BLUR_COL(w, 24)
 #undef DVO_BLUR_COL
