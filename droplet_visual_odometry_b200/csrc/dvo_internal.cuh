@@ -122,7 +122,7 @@ struct IngestParams {
     double k[8];             // k1 k2 p1 p2 k3 k4 k5 k6
 };
 struct IngestBuffers {
-    uint2* map = nullptr;        // [h][w]: x = (u16)sx | (u16)sy << 16 (integer source position, int16), y = fy << 5 | fx
+    uint4* map = nullptr;        // [h][w]: x = (u16)sx | (u16)sy << 16 (integer source position, int16), y = w00 | w01 << 16, z = w10 | w11 << 16
     const uint2* wtab = nullptr; // [32*32]: four uint16 bilinear weights (taps 00 01 10 11), sum 32768
     int channels = 0;            // 0 = ingest disabled (frames are already grey + undistorted); 1 grey, 3 BGR
 };

@@ -993,16 +993,16 @@ __global__ void __launch_bounds__(256) k_build_undistort_map(OrbGeom g, IngestBu
     const double u = dadd(dmul(p.fx, xd), p.cx), v = dadd(dmul(p.fy, yd), p.cy);
     const int iu = __double2int_rn(dmul(u, 32.0)), iv = __double2int_rn(dmul(v, 32.0));
     const int sx = max(-32768, min(32767, iu >> 5)), sy = max(-32768, min(32767, iv >> 5));
-    ib.map[(size_t)i * w + j] = make_uint2((uint32_t)(uint16_t)(short)sx | ((uint32_t)(uint16_t)(short)sy << 16),
-                                           (uint32_t)(((iv & 31) << 5) | (iu & 31)));
+    const uint2 wq = __ldg(ib.wtab + (((iv & 31) << 5) | (iu & 31)));      // the four tap weights ride along in the map entry
+    ib.map[(size_t)i * w + j] = make_uint4((uint32_t)(uint16_t)(short)sx | ((uint32_t)(uint16_t)(short)sy << 16), wq.x, wq.y, 0u);
 }
 
 template <int kChannels>
-__device__ __forceinline__ int ingest_tap(const uint8_t* frame, size_t pitch, int w, int h, int y, int x) {
+__device__ __forceinline__ uint32_t ingest_tap(const uint8_t* frame, size_t pitch, int w, int h, int y, int x) {
     if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return 0;      // BORDER_CONSTANT, value 0
     const uint8_t* q = frame + (size_t)y * pitch + (size_t)x * kChannels;
     if (kChannels == 1) return q[0];
-    return (3735 * (int)q[0] + 19235 * (int)q[1] + 9798 * (int)q[2] + (1 << 14)) >> 15;
+    return (uint32_t)((3735 * (int)q[0] + 19235 * (int)q[1] + 9798 * (int)q[2] + (1 << 14)) >> 15);
 }
 
 template <int kChannels>
@@ -1018,15 +1018,14 @@ __global__ void __launch_bounds__(256) k_ingest(OrbGeom g, OrbBuffers b, IngestB
     for (int k = 0; k < 4; ++k) {
         const int x = x4 + k;
         if (x >= l0.w) break;
-        const uint2 m = __ldg(ib.map + (size_t)y * l0.w + x);
+        const uint4 m = __ldg(ib.map + (size_t)y * l0.w + x);
         const int sx = (int)(short)(m.x & 0xFFFFu), sy = (int)(short)(m.x >> 16);
-        const uint2 wq = __ldg(ib.wtab + m.y);
-        const int w00 = (int)(wq.x & 0xFFFFu), w01 = (int)(wq.x >> 16);      // unsigned: the integer-position entry is 32768
-        const int w10 = (int)(wq.y & 0xFFFFu), w11 = (int)(wq.y >> 16);
-        const int acc = ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx) * w00 +
-                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx + 1) * w01 +
-                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx) * w10 +
-                        ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx + 1) * w11;
+        // two taps per DP2A: (w00, w01) x (p00, p01) and (w10, w11) x (p10, p11); weights are uint16 (0 .. 32768)
+        const uint32_t t0 = ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx) |
+                            (ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy, sx + 1) << 8);
+        const uint32_t t1 = ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx) |
+                            (ingest_tap<kChannels>(frame, pitch, l0.w, l0.h, sy + 1, sx + 1) << 8);
+        const int acc = (int)__dp2a_lo(m.y, t0, __dp2a_lo(m.z, t1, 0u));
         const int v = max(0, min(255, (acc + (1 << 14)) >> 15));
         out |= (uint32_t)v << (8 * k);
     }
