@@ -243,7 +243,7 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, K_steps, W_steps = a.batch, a.steps, a.warmup
+    B, K_steps, W_steps = a.batch, max(a.steps, 1), max(a.warmup, 3)      # timing rule: at least 3 untimed warm-up steps
     n_frames = (K_steps + W_steps) * B + 1
     frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * 5000)
     ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local)
