@@ -33,6 +33,7 @@ struct dvo_ctx {
     uint32_t* d_resizeTab = nullptr;
     double* d_K = nullptr;
     dvo_pose* h_poseStage = nullptr;   // pinned staging for the host sequence runner
+    size_t poseStageCap = 0;
     uint8_t* h_frameStage = nullptr;
     long long launchBase = 0;
     int carrySlot = -1;                // slot holding the last frame of the previous dvo_sequence_step
@@ -810,17 +811,32 @@ int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch
         return DVO_E_INVALID;
     }
     const int B = ctx->nSlots - 1;   // new frames per batch after the first
+    // Host destination: the records go through a pinned staging array, so the per-batch D2H copies stay asynchronous (a
+    // copy into pageable memory would block the host and with it the overlap between batches).
+    dvo_pose* dst = poses;
+    if (kind == 1) {
+        const size_t need = (size_t)(n_frames - 1);
+        if (ctx->poseStageCap < need) {
+            if (ctx->h_poseStage) { CK(cudaStreamSynchronize((cudaStream_t)stream)); CK(cudaFreeHost(ctx->h_poseStage)); ctx->h_poseStage = nullptr; }
+            CK(cudaMallocHost(&ctx->h_poseStage, need * sizeof(dvo_pose)));
+            ctx->poseStageCap = need;
+        }
+        dst = ctx->h_poseStage;
+    }
     int done = std::min(n_frames, ctx->nSlots);
-    int rc = dvo_sequence_step(ctx, frames, done, pitch, frame_stride, K, poses, kind, 1, stream);
+    int rc = dvo_sequence_step(ctx, frames, done, pitch, frame_stride, K, dst, kind, 1, stream);
     if (rc < 0) return rc;
     while (done < n_frames) {
         int nb = std::min(B, n_frames - done);
-        rc = dvo_sequence_step(ctx, frames + (size_t)done * frame_stride, nb, pitch, frame_stride, K, poses + (done - 1), kind, 0, stream);
+        rc = dvo_sequence_step(ctx, frames + (size_t)done * frame_stride, nb, pitch, frame_stride, K, dst + (done - 1), kind, 0, stream);
         if (rc < 0) return rc;
         done += nb;
     }
     if ((rc = dvo_sequence_flush(ctx, stream)) != 0) return rc;
-    if (kind == 1) CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (kind == 1) {
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        memcpy(poses, dst, (size_t)(n_frames - 1) * sizeof(dvo_pose));
+    }
     return DVO_OK;
 }
 
