@@ -185,13 +185,14 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     constexpr int kQuadsX = 34, kQuadsY = kTileH + 2, kRowsPerSweep = 7;
     {
         const int qx = tid % kQuadsX, qrow = tid / kQuadsX;          // qrow == 7 for the 18 spare threads
-        // byte k of this thread's quads is a ring column inside the level's FAST domain?
-        uint32_t colmask = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int rc = 12 + 4 * qx + k, sx = x0 - kFastHaloL + rc;
-            if (rc >= 15 && rc <= 144 && sx >= 3 && sx < lv.w - 3) colmask |= 0x80u << (8 * k);
-        }
+        // bytes of this thread's quads that are ring columns (raw 15..144) inside the level's FAST domain (3 <= x < w - 3):
+        // cut the leading / trailing bytes outside [cLo, cHi]
+        const int rc0 = 12 + 4 * qx;
+        const int cLo = max(15, 3 - (x0 - kFastHaloL)), cHi = min(144, lv.w - 4 - (x0 - kFastHaloL));
+        const int nLead = min(max(cLo - rc0, 0), 4), nTrail = min(max(rc0 + 3 - cHi, 0), 4);
+        uint32_t colmask = 0x80808080u;
+        colmask &= nLead >= 4 ? 0u : (0xFFFFFFFFu << (8 * nLead));
+        colmask &= nTrail >= 4 ? 0u : (0xFFFFFFFFu >> (8 * nTrail));
         if (qrow >= kRowsPerSweep) colmask = 0;
         constexpr int kSweeps = (kQuadsY + kRowsPerSweep - 1) / kRowsPerSweep;
         uint32_t passw[kSweeps];
@@ -286,12 +287,15 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         const int ry = code / kFastBoxW, rx = code - ry * kFastBoxW;
         const int cy = ry - 3, cx = rx - 15;                   // ring coordinates: tile pixel (cx-1, cy-1)
         const int x = x0 + cx - 1, y = y0 + cy - 1;
-        if (cx < 1 || cx > kTileW || cy < 1 || cy > kTileH) continue;
-        if (x < border || x >= lv.w - border || y < border || y >= lv.h - border) continue;
+        // inside the tile (ring positions only lend their scores) and inside the 31-px border: four unsigned range checks
+        const bool in = ((unsigned)(cx - 1) < (unsigned)kTileW) & ((unsigned)(cy - 1) < (unsigned)kTileH) &
+                        ((unsigned)(x - border) < (unsigned)max(lv.w - 2 * border, 0)) &
+                        ((unsigned)(y - border) < (unsigned)max(lv.h - 2 * border, 0));
+        if (!in) continue;
         const uint8_t* q = sc + cy * 136 + cx;
         const int sv = *q;
-        const bool keep = sv > q[-1] && sv > q[1] && sv > q[-136 - 1] && sv > q[-136] && sv > q[-136 + 1] && sv > q[136 - 1] &&
-                          sv > q[136] && sv > q[136 + 1];
+        const int nmax = imax3(imax3(q[-136 - 1], q[-136], q[-136 + 1]), imax3(q[-1], q[1], q[136 - 1]), imax(q[136], q[136 + 1]));
+        const bool keep = sv > nmax;
         if (keep) {
             outmap[(cy - 1) * kTileW + (cx - 1)] = (uint8_t)sv;
             atomicAdd(&s_rowcnt[cy - 1], 1);
