@@ -11,6 +11,7 @@ long long orb_launch_count();
 long long pair_launch_count();
 void orb_kernels_init();
 void pair_kernels_init(int sortBytes);
+void pair_kernels_init_exhaustive(int rngCount);
 void prof_enable(bool on);
 bool prof_enabled();
 void prof_collect(double* ms, int* count, int n);
@@ -238,7 +239,7 @@ void dvo_default_config(dvo_config* c) {
     c->max_frames = 2;
     c->matcher = DVO_MATCH_CROSSCHECK;
     c->ransac_max_iters = 1000; c->ransac_prob = 0.999; c->ransac_threshold = 1.0;
-    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1; c->pipeline = 1;
+    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1; c->pipeline = 1; c->ransac_exhaustive = 0;
 }
 
 int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
@@ -303,6 +304,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     while (pg.sortCap < g.maxkp) pg.sortCap <<= 1;
     pg.matcher = cfg->matcher;
     pg.maxIters = cfg->ransac_max_iters;
+    pg.exhaustive = cfg->ransac_exhaustive != 0;
     pg.prob = cfg->ransac_prob;
     pg.threshold = cfg->ransac_threshold;
     pg.distThresh = cfg->distance_thresh;
@@ -317,6 +319,25 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     DA(pb.ptsCur, P * M * 2);
     DA(pb.normPts, P * M * 4);
     DA(pb.samples, P * (size_t)pg.maxIters * 5);
+    if (pg.exhaustive || (g.maxkp >= 1500 && P <= 8)) {
+        // cv::RNG(-1) state table: 16 draws of margin per iteration (5 are needed, more only after duplicate redraws)
+        pg.rngCount = std::min(16 * pg.maxIters, 200 * 1024);
+        std::vector<unsigned long long> st(pg.rngCount);
+        unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+        for (int i = 0; i < pg.rngCount; ++i) {
+            state = (unsigned long long)(uint32_t)state * 4164903690ull + (state >> 32);
+            st[i] = state;
+        }
+        unsigned long long* d_st = nullptr;
+        DA(d_st, st.size());
+        CK(cudaMemcpy(d_st, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        pb.rngStates = d_st;
+        DA(pb.exStart, P * (size_t)pg.maxIters);
+        pair_kernels_init_exhaustive(pg.rngCount);
+        DA(pb.exModels, P * (size_t)pg.maxIters * kMaxModels * 9);
+        DA(pb.exCount, P * (size_t)pg.maxIters);
+        DA(pb.exGood, P * (size_t)pg.maxIters * kMaxModels);
+    }
     DA(pb.ransacState, P * 8);
     DA(pb.bestE, P * 9);
     DA(pb.ransacMask, P * M);

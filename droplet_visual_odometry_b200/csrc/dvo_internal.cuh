@@ -89,6 +89,8 @@ struct PairGeom {
     int sortCap;          // power of two >= maxkp
     int matcher;          // 0 crosscheck, 1 knn ratio + reverse check
     int maxIters;
+    int exhaustive;       // score all maxIters hypotheses (no adaptive stop)
+    int rngCount;         // entries of PairBuffers::rngStates
     double prob, threshold, distThresh;
     float ratio;
 };
@@ -111,6 +113,11 @@ struct PairBuffers {
     double* bestE;        // [pairs][9]
     uint8_t* ransacMask;  // [pairs][maxkp]
     uint8_t* poseMask;    // [pairs][maxkp]
+    const unsigned long long* rngStates;   // [rngCount] cv::RNG(-1) states after 1, 2, ... steps (exhaustive mode only)
+    int* exStart;         // [pairs][maxIters] offset of each iteration's first draw in rngStates
+    double* exModels;     // [pairs][maxIters][10][9]  exhaustive mode only
+    int* exCount;         // [pairs][maxIters]
+    int* exGood;          // [pairs][maxIters][10]
     dvo_pose* poses;      // [pairs]
     PoseScratch* poseScratch;   // [pairs]
 };

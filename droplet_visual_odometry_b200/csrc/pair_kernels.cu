@@ -12,6 +12,7 @@
 #include "mathcore.cuh"
 #include "fivepoint_group.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 
 namespace dvo {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
 //             discarded, so E, mask and iteration count are the ones the sequential loop produces)
 // then the final mask and the SVD of E for recoverPose.  No launch is spent on pairs that have already stopped.
 constexpr int kRansacGroups = 16;
+constexpr int kWindowedMaxPairs = 8;      // at most this many pairs: windowed whole-GPU speculation instead of one CTA per pair
 constexpr int kRansacThreads = kRansacGroups * kGroupLanes;
 
 struct RansacShared {
@@ -206,6 +208,45 @@ struct RansacShared {
     int partial[kRansacGroups][kMaxModels];      // cluster mode: this CTA's share of the inlier counts
     int maxGood, niters, done, it0, bestIter, bestModel, hasBest, cnt;
 };
+
+// Final mask of the winning model and SVD(E) -> R1, R2, t (first half of recoverPose); whole CTA, any block size.
+// bestE: 9 doubles in shared memory; s_cnt: a shared int.
+__device__ void ransac_finish(const PairGeom& pg, const PairBuffers& pb, PoseScratch* ps, int pair, int M, const double* bestE,
+                              int hasBest, float t32, int* s_cnt) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double T = (double)t32, tlo = T * (1.0 - 1e-6), thi = T * (1.0 + 1e-6);
+    PoseScratch& sc = ps[pair];
+    uint8_t* mask = pb.ransacMask + (size_t)pair * pg.maxkp;
+    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+    if (tid == 0) {
+        *s_cnt = 0;
+        for (int k = 0; k < 4; ++k) sc.good[k] = 0;
+    }
+    __syncthreads();
+    if (!hasBest) {
+        for (int i = tid; i < M; i += blockDim.x) mask[i] = 0;
+        if (tid == 0) sc.nInl = 0;
+        return;
+    }
+    double E[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) E[j] = bestE[j];
+    if (tid < 9) pb.bestE[pair * 9 + tid] = E[tid];
+    int local = 0;
+    for (int i = tid; i < M; i += blockDim.x) {
+        const double4 p = np4[i];
+        const int in = sampson_inlier(E, p.x, p.y, p.z, p.w, t32, tlo, thi) ? 1 : 0;
+        mask[i] = (uint8_t)in;
+        local += in;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0) atomicAdd(s_cnt, local);
+    __syncthreads();
+    if (tid == 0) {
+        sc.nInl = *s_cnt;
+        decompose_essential(E, sc.R1, sc.R2, sc.t);
+    }
+}
 
 // kCluster: a thread-block cluster of up to 8 CTAs works on ONE pair (few pairs, many correspondences -- BASELINE configs[4]).
 // Every CTA runs the identical, deterministic control flow (RNG, solves, replay), so the loop state stays in lock-step
@@ -335,40 +376,255 @@ __global__ void __launch_bounds__(kRansacThreads, 2) k_ransac(PairGeom pg, PairB
     }
     // ---- final state, mask of the winning model, SVD(E) -> R1, R2, t  (first half of recoverPose)
     if (kCluster && crank != 0) return;      // lock-step loop: the last cluster barrier is behind every CTA
-    PoseScratch& sc = ps[pair];
-    uint8_t* mask = pb.ransacMask + (size_t)pair * pg.maxkp;
-    const int hasBest = sh.hasBest;
     if (tid == 0) {
         rs[RS_MAXGOOD] = sh.maxGood; rs[RS_NITERS] = sh.niters; rs[RS_DONE] = 1;
-        rs[RS_BESTITER] = sh.bestIter; rs[RS_BESTMODEL] = sh.bestModel; rs[RS_HASBEST] = hasBest;
+        rs[RS_BESTITER] = sh.bestIter; rs[RS_BESTMODEL] = sh.bestModel; rs[RS_HASBEST] = sh.hasBest;
         rs[RS_RNG_LO] = (int)(uint32_t)sh.rng; rs[RS_RNG_HI] = (int)(uint32_t)(sh.rng >> 32);
-        sh.cnt = 0;
-        for (int k = 0; k < 4; ++k) sc.good[k] = 0;
+    }
+    ransac_finish(pg, pb, ps, pair, M, sh.bestE, sh.hasBest, t32, &sh.cnt);
+}
+
+// ================================================================================================ exhaustive RANSAC
+// "All hypotheses scored" (dvo_config.ransac_exhaustive, BASELINE configs[4]): no adaptive stop, so nothing is sequential
+// except the cv::RNG stream -- the whole GPU solves and scores:
+//   k_ex_samples   one thread per pair walks the RNG (5 distinct positions per iteration, single-index redraw)
+//   k_ex_solve     one 16-lane group per hypothesis (fivepoint_group.cuh), models to global memory
+//   k_ex_score     CTA = 16 hypotheses x one slice of the correspondences: models in shared memory, matches in registers,
+//                  warp-reduced counts, one atomicAdd per (CTA, model)
+//   k_ex_pick      first model (iteration, then solver order) with the highest count > 4 -- what cv2's strict '>' update keeps
+//                  when the iteration count never shrinks -- then mask + SVD(E)
+// The cv::RNG stream does not depend on the data (cv2 reseeds it with -1 for every call), only the use made of it does
+// (value % M, redraw on a duplicate).  So the 64-bit states are tabulated once per context on the host (rngStates), and a
+// call only has to find where each iteration starts in that stream:
+//   1. every thread simulates "one iteration starting at offset o" for its share of offsets -> draws consumed, len[o]
+//   2. one thread follows o -> o + len[o] for maxIters steps (a shared-memory load per step)
+//   3. every thread re-simulates its iterations from their start offsets and writes the 5 positions
+// A serial walk of the generator itself took 3.4 ms for 4096 iterations; this takes ~0.1 ms.
+__device__ __forceinline__ int ex_sample_from(const unsigned long long* states, int o, int nStates, uint32_t M, int* idx) {
+    int i = 0, used = 0;
+    while (i < 5 && o + used < nStates) {
+        const int v = (int)((uint32_t)states[o + used] % M);
+        ++used;
+        bool dup = false;
+        for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
+        if (!dup) idx[i++] = v;
+    }
+    return i == 5 ? used : 0;      // 0: ran off the table (cannot happen with the 16x margin unless M is tiny)
+}
+
+__global__ void __launch_bounds__(1024) k_ex_samples(PairGeom pg, PairBuffers pb, int pair0) {
+    extern __shared__ unsigned char s_len[];           // [nStates] draws consumed by an iteration starting here
+    __shared__ int s_ok;
+    const int pair = pair0 + blockIdx.x;
+    const int M = pb.matchCount[pair];
+    if (M <= 5) return;
+    const int nStates = pg.rngCount;
+    int* starts = pb.exStart + (size_t)pair * pg.maxIters;
+    int* out = pb.samples + (size_t)pair * pg.maxIters * 5;
+    if (threadIdx.x == 0) s_ok = 1;
+    for (int o = threadIdx.x; o < nStates; o += blockDim.x) {
+        int idx[5];
+        s_len[o] = (unsigned char)min(ex_sample_from(pb.rngStates, o, nStates, (uint32_t)M, idx), 255);
     }
     __syncthreads();
-    if (!hasBest) {
-        for (int i = tid; i < M; i += kRansacThreads) mask[i] = 0;
-        if (tid == 0) sc.nInl = 0;
-        return;
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int it = 0; it < pg.maxIters; ++it) {
+            starts[it] = o;
+            const int l = o < nStates ? s_len[o] : 0;
+            if (l == 0 || l == 255) { s_ok = 0; break; }
+            o += l;
+        }
     }
-    double E[9];
+    __syncthreads();
+    if (s_ok) {
+        for (int it = threadIdx.x; it < pg.maxIters; it += blockDim.x) {
+            int idx[5];
+            ex_sample_from(pb.rngStates, starts[it], nStates, (uint32_t)M, idx);
+            for (int k = 0; k < 5; ++k) out[it * 5 + k] = idx[k];
+        }
+    } else if (threadIdx.x == 0) {      // table exhausted (M barely above 5): plain serial walk of the generator
+        uint64_t state = 0xFFFFFFFFFFFFFFFFull;
+        for (int it = 0; it < pg.maxIters; ++it) {
+            int idx[5];
+            int i = 0;
+            while (i < 5) {
+                const int v = (int)(cvrng_next(state) % (uint32_t)M);
+                bool dup = false;
+                for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
+                if (dup) continue;
+                idx[i++] = v;
+            }
+            for (int k = 0; k < 5; ++k) out[it * 5 + k] = idx[k];
+        }
+    }
+}
+
+// Window [it0, it0 + nIt) of iterations; a pair whose loop has already stopped (RS_DONE) is skipped, and so are iterations
+// past the current adaptive bound (RS_NITERS) -- both only ever shrink.
+__global__ void __launch_bounds__(kRansacThreads, 2) k_ex_solve(PairGeom pg, PairBuffers pb, int pair0, int it0, int nIt) {
+    __shared__ SolveScratch scratch[kRansacGroups];
+    const int pair = pair0 + blockIdx.y;
+    const int* rs = pb.ransacState + pair * 8;
+    if (rs[RS_DONE]) return;
+    const int itEnd = min(min(it0 + nIt, pg.maxIters), rs[RS_NITERS]);
+    const int M = pb.matchCount[pair];
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid / kGroupLanes, gl = tid & (kGroupLanes - 1);
+    const unsigned gmask = 0xFFFFu << (lane & 16);
+    const int itBase = it0 + blockIdx.x * kRansacGroups;
+    const int it = itBase + grp;
+    int* good = pb.exGood + ((size_t)pair * pg.maxIters + itBase) * kMaxModels;
+    for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads)
+        if (itBase + i / kMaxModels < pg.maxIters) good[i] = 0;
+    if (it >= itEnd) return;
+    if (M <= 5) { if (gl == 0) pb.exCount[(size_t)pair * pg.maxIters + it] = 0; return; }
+    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+    const int* smp = pb.samples + ((size_t)pair * pg.maxIters + it) * 5;
+    double x1[10], x2[10];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) E[j] = sh.bestE[j];
-    if (tid < 9) pb.bestE[pair * 9 + tid] = E[tid];
-    int local = 0;
-    for (int i = tid; i < M; i += kRansacThreads) {
-        const double4 p = np4[i];
-        const int in = sampson_inlier(E, p.x, p.y, p.z, p.w, t32, tlo, thi) ? 1 : 0;
-        mask[i] = (uint8_t)in;
-        local += in;
+    for (int k = 0; k < 5; ++k) {
+        const double4 p = np4[smp[k]];
+        x1[2 * k] = p.x; x1[2 * k + 1] = p.y;
+        x2[2 * k] = p.z; x2[2 * k + 1] = p.w;
     }
-    local = __reduce_add_sync(0xffffffffu, local);
-    if (lane == 0) atomicAdd(&sh.cnt, local);
+    double* models = pb.exModels + ((size_t)pair * pg.maxIters + it) * kMaxModels * 9;
+    const int n = five_point_solve_group(x1, x2, scratch[grp], models, gmask);
+    if (gl == 0) pb.exCount[(size_t)pair * pg.maxIters + it] = n;
+}
+
+__global__ void __launch_bounds__(kRansacThreads) k_ex_score(PairGeom pg, PairBuffers pb, int pair0, int itw0, int nItw, float t32) {
+    __shared__ double s_models[kRansacGroups][kMaxModels][9];
+    __shared__ int s_count[kRansacGroups];
+    __shared__ int s_good[kRansacGroups][kMaxModels];
+    const int pair = pair0 + blockIdx.z;
+    const int M = pb.matchCount[pair];
+    const int* rs = pb.ransacState + pair * 8;
+    if (M <= 5 || rs[RS_DONE]) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int it0 = itw0 + blockIdx.x * kRansacGroups;
+    const int nIt = min(kRansacGroups, min(min(itw0 + nItw, pg.maxIters), rs[RS_NITERS]) - it0);
+    if (nIt <= 0) return;
+    const double T = (double)t32, tlo = T * (1.0 - 1e-6), thi = T * (1.0 + 1e-6);
+    const double* gm = pb.exModels + ((size_t)pair * pg.maxIters + it0) * kMaxModels * 9;
+    for (int i = tid; i < nIt * kMaxModels * 9; i += kRansacThreads) (&s_models[0][0][0])[i] = gm[i];
+    for (int i = tid; i < kRansacGroups * kMaxModels; i += kRansacThreads) (&s_good[0][0])[i] = 0;
+    if (tid < nIt) s_count[tid] = pb.exCount[(size_t)pair * pg.maxIters + it0 + tid];
     __syncthreads();
-    if (tid == 0) {
-        sc.nInl = sh.cnt;
-        decompose_essential(E, sc.R1, sc.R2, sc.t);
+    const double4* np4 = reinterpret_cast<const double4*>(pb.normPts + (size_t)pair * pg.maxkp * 4);
+    const int per = (M + gridDim.y - 1) / gridDim.y;
+    const int mBeg = min(M, (int)blockIdx.y * per), mEnd = min(M, mBeg + per);
+    for (int base = mBeg; base < mEnd; base += 2 * kRansacThreads) {
+        const int i0 = base + tid, i1 = base + kRansacThreads + tid;
+        const bool v0 = i0 < mEnd, v1 = i1 < mEnd;
+        const double4 p0 = v0 ? np4[i0] : make_double4(0, 0, 0, 0);
+        const double4 p1 = v1 ? np4[i1] : make_double4(0, 0, 0, 0);
+        for (int h = 0; h < nIt; ++h) {
+            const int nm = s_count[h];
+            for (int k = 0; k < nm; ++k) {
+                double E[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) E[j] = s_models[h][k][j];
+                int good = (v0 && sampson_inlier(E, p0.x, p0.y, p0.z, p0.w, t32, tlo, thi)) ? 1 : 0;
+                good += (v1 && sampson_inlier(E, p1.x, p1.y, p1.z, p1.w, t32, tlo, thi)) ? 1 : 0;
+                good = __reduce_add_sync(0xffffffffu, good);
+                if (lane == 0 && good) atomicAdd(&s_good[h][k], good);
+            }
+        }
     }
+    __syncthreads();
+    int* gg = pb.exGood + ((size_t)pair * pg.maxIters + it0) * kMaxModels;
+    for (int i = tid; i < nIt * kMaxModels; i += kRansacThreads) {
+        const int v = (&s_good[0][0])[i];
+        if (v) atomicAdd(gg + i, v);
+    }
+}
+
+// cv2's update rule over one window of already solved and scored iterations, in order (one thread per pair: the rule is
+// sequential, the window is short).  Sets RS_DONE when the adaptive bound has been reached.
+__global__ void k_ex_replay(PairGeom pg, PairBuffers pb, int pair0, int nPairs, int it0, int nIt) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= nPairs) return;
+    const int pair = pair0 + pi;
+    int* rs = pb.ransacState + pair * 8;
+    if (rs[RS_DONE]) return;
+    const int M = pb.matchCount[pair];
+    int maxGood = rs[RS_MAXGOOD], niters = rs[RS_NITERS];
+    const int itEnd = min(it0 + nIt, pg.maxIters);
+    const int* cnt = pb.exCount + (size_t)pair * pg.maxIters;
+    const int* good = pb.exGood + (size_t)pair * pg.maxIters * kMaxModels;
+    int it = it0;
+    for (; it < itEnd; ++it) {
+        if (it >= niters) break;
+        const int nm = cnt[it];
+        for (int k = 0; k < nm; ++k) {
+            const int g = good[it * kMaxModels + k];
+            if (g > max(maxGood, 4)) {
+                maxGood = g;
+                const double* Eg = pb.exModels + ((size_t)pair * pg.maxIters * kMaxModels + (size_t)it * kMaxModels + k) * 9;
+                for (int j = 0; j < 9; ++j) pb.bestE[pair * 9 + j] = Eg[j];
+                rs[RS_BESTITER] = it;
+                rs[RS_BESTMODEL] = k;
+                rs[RS_HASBEST] = 1;
+                niters = ransac_update_num_iters(pg.prob, (double)(M - g) / M, 5, niters);
+            }
+        }
+    }
+    rs[RS_MAXGOOD] = maxGood;
+    rs[RS_NITERS] = niters;
+    if (it >= niters || it >= pg.maxIters) rs[RS_DONE] = 1;
+}
+
+__global__ void __launch_bounds__(1024) k_ex_finish(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
+    __shared__ double s_E[9];
+    __shared__ int s_cnt;
+    const int pair = pair0 + blockIdx.x;
+    int* rs = pb.ransacState + pair * 8;
+    const int hasBest = rs[RS_HASBEST];
+    if (threadIdx.x < 9) s_E[threadIdx.x] = hasBest ? pb.bestE[pair * 9 + threadIdx.x] : 0.0;
+    if (threadIdx.x == 0) rs[RS_DONE] = 1;
+    __syncthreads();
+    ransac_finish(pg, pb, ps, pair, pb.matchCount[pair], s_E, hasBest, t32, &s_cnt);
+}
+
+__global__ void __launch_bounds__(1024) k_ex_pick(PairGeom pg, PairBuffers pb, PoseScratch* ps, int pair0, float t32) {
+    __shared__ unsigned long long s_best;
+    __shared__ double s_E[9];
+    __shared__ int s_cnt;
+    const int pair = pair0 + blockIdx.x;
+    int* rs = pb.ransacState + pair * 8;
+    const int M = pb.matchCount[pair];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_best = 0ull;
+    __syncthreads();
+    // key = count << 32 | ~flat index: the maximum is the highest count, and among equals the earliest (iteration, model)
+    unsigned long long best = 0ull;
+    if (M > 5) {
+        const int* cnt = pb.exCount + (size_t)pair * pg.maxIters;
+        const int* good = pb.exGood + (size_t)pair * pg.maxIters * kMaxModels;
+        for (int f = tid; f < pg.maxIters * kMaxModels; f += blockDim.x) {
+            const int it = f / kMaxModels, k = f - it * kMaxModels;
+            if (k >= cnt[it]) continue;
+            const int g = good[f];
+            if (g > 4) best = max(best, ((unsigned long long)(uint32_t)g << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)f));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0 && best) atomicMax(&s_best, best);
+    __syncthreads();
+    const unsigned long long b = s_best;
+    const int hasBest = b != 0ull;
+    const int f = hasBest ? (int)(0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)) : -1;
+    if (hasBest && tid < 9) s_E[tid] = pb.exModels[((size_t)pair * pg.maxIters * kMaxModels + f) * 9 + tid];
+    if (tid == 0) {
+        rs[RS_MAXGOOD] = hasBest ? (int)(b >> 32) : 0;
+        rs[RS_NITERS] = pg.maxIters;
+        rs[RS_DONE] = 1;
+        rs[RS_BESTITER] = hasBest ? f / kMaxModels : -1;
+        rs[RS_BESTMODEL] = hasBest ? f % kMaxModels : -1;
+        rs[RS_HASBEST] = hasBest;
+    }
+    __syncthreads();
+    ransac_finish(pg, pb, ps, pair, M, s_E, hasBest, t32, &s_cnt);
 }
 
 // ================================================================================================ recoverPose
@@ -448,6 +704,10 @@ __global__ void __launch_bounds__(256) k_pose_final(OrbGeom og, OrbBuffers ob, P
 static long long g_pair_launches = 0;
 long long pair_launch_count() { return g_pair_launches; }
 
+void pair_kernels_init_exhaustive(int rngCount) {
+    cudaFuncSetAttribute(k_ex_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, rngCount);
+}
+
 void pair_kernels_init(int sortBytes) {
     // contexts too large for the in-smem sort (points-only use) never launch k_match_sort: dvo_pairs refuses them
     if (sortBytes > 48 * 1024 && sortBytes <= 200 * 1024)
@@ -487,7 +747,38 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
     const double thr = pg.threshold / ((fx + fy) / 2.0);
     const float t32 = (float)(thr * thr);
     PoseScratch* ps = pb.poseScratch;
-    {
+    if (pg.exhaustive) {
+        ProfScope ps_(PF_RANSAC, st);
+        const int chunks = (pg.maxIters + kRansacGroups - 1) / kRansacGroups;
+        int slices = 1;      // enough CTAs to fill the machine a few times over, at least ~2048 correspondences per slice
+        while (slices < 64 && (long long)chunks * nPairs * slices < 148 * 8 && pg.maxkp / (slices * 2) >= 2048) slices *= 2;
+        k_ex_samples<<<nPairs, 1024, pg.rngCount, st>>>(pg, pb, pair0);
+        k_ex_solve<<<dim3(chunks, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, 0, pg.maxIters);
+        k_ex_score<<<dim3(chunks, slices, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, 0, pg.maxIters, t32);
+        k_ex_pick<<<nPairs, 1024, 0, st>>>(pg, pb, ps, pair0, t32);
+        g_pair_launches += 4;
+        debug_sync("k_ex_*", st);
+    } else if (pb.exModels != nullptr && nPairs <= kWindowedMaxPairs && getenv("DVO_NO_WINDOWED") == nullptr) {
+        // Few pairs (BASELINE configs[3], [4]): cv2's adaptive loop with speculation across the whole GPU -- windows of
+        // iterations are solved and scored by the batched kernels above, then replayed in order; windows grow 128, 384,
+        // 1536, ... so the typical pair (about a hundred iterations) stops after the first.
+        ProfScope ps_(PF_RANSAC, st);
+        k_ex_samples<<<nPairs, 1024, pg.rngCount, st>>>(pg, pb, pair0);
+        ++g_pair_launches;
+        for (int w0 = 0, wn = 128; w0 < pg.maxIters; w0 += wn, wn *= 3) {
+            const int n = std::min(wn, pg.maxIters - w0);
+            const int chunks = (n + kRansacGroups - 1) / kRansacGroups;
+            int slices = 1;
+            while (slices < 64 && (long long)chunks * nPairs * slices < 148 * 4 && pg.maxkp / (slices * 2) >= 512) slices *= 2;
+            k_ex_solve<<<dim3(chunks, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, w0, n);
+            k_ex_score<<<dim3(chunks, slices, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, w0, n, t32);
+            k_ex_replay<<<(nPairs + 31) / 32, 32, 0, st>>>(pg, pb, pair0, nPairs, w0, n);
+            g_pair_launches += 3;
+        }
+        k_ex_finish<<<nPairs, 1024, 0, st>>>(pg, pb, ps, pair0, t32);
+        ++g_pair_launches;
+        debug_sync("k_ex_window", st);
+    } else {
         ProfScope ps_(PF_RANSAC, st);
         // few pairs with many correspondences: a cluster of CTAs per pair shares the scoring (DSMEM count reduction)
         int csize = 1;

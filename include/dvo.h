@@ -58,6 +58,9 @@ typedef struct dvo_config {
     int pipeline;            /* 1 (default): dvo_sequence / dvo_sequence_step overlap the ORB stage of one batch with the
                                 pair stage of the previous one on internal streams (second buffer set, allocated on
                                 first use); 0: every stage in order on the caller's stream                        */
+    int ransac_exhaustive;   /* 0 (default): cv.findEssentialMat's adaptive stop.  1: every one of ransac_max_iters hypotheses
+                                is solved and scored (whole-GPU batched solve + Sampson sweep; BASELINE configs[4] "all
+                                hypotheses scored"); the first model with the highest inlier count wins                */
 } dvo_config;
 
 /* Result of one frame pair: what cv.findEssentialMat + cv.recoverPose return (visual_odometry_v3.py:297-306). */

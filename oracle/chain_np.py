@@ -12,12 +12,12 @@ def orb_features(img, nfeatures=500, nlevels=8):
     return {k: r[k] for k in ("pt", "size", "angle", "response", "octave", "desc", "lvl_xy")}
 
 
-def pose_from_points(p_prev, p_cur, K, max_iters=1000):
+def pose_from_points(p_prev, p_cur, K, max_iters=1000, exhaustive=False):
     out = {"status": 0, "E": None, "ransac_mask": None, "R": None, "t": None, "pose_mask": None, "good": 0}
     if len(p_prev) < 5:
         out["status"] = -1
         return out
-    E, mask = pose_np.find_essential_mat(p_prev, p_cur, K, 0.999, 1.0, max_iters)
+    E, mask = pose_np.find_essential_mat(p_prev, p_cur, K, 0.999, 1.0, max_iters, exhaustive=exhaustive)
     if E is None:
         out["status"] = -2
         return out

@@ -292,8 +292,11 @@ def sampson_errors(E: np.ndarray, x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
         return (x2tEx1 * x2tEx1 / den).astype(np.float32)
 
 
-def find_essential_mat(p1, p2, K, prob=0.999, threshold=1.0, max_iters=1000, solver=five_point, return_trace=False):
-    """cv2.findEssentialMat(p1, p2, K, RANSAC, prob, threshold, maxIters) -> (E 3x3 or None, mask (N,) u8)."""
+def find_essential_mat(p1, p2, K, prob=0.999, threshold=1.0, max_iters=1000, solver=five_point, return_trace=False,
+                       exhaustive=False):
+    """cv2.findEssentialMat(p1, p2, K, RANSAC, prob, threshold, maxIters) -> (E 3x3 or None, mask (N,) u8).
+    ``exhaustive``: never shrink the iteration count (all max_iters hypotheses are scored, first best wins) -- the
+    "all hypotheses scored" mode of BASELINE configs[4]; cv2 itself cannot be made to do this (it asserts prob < 1)."""
     x1 = normalize_points(p1, K)
     x2 = normalize_points(p2, K)
     n = len(x1)
@@ -322,7 +325,8 @@ def find_essential_mat(p1, p2, K, prob=0.999, threshold=1.0, max_iters=1000, sol
             trace["models_scored"] += 1
             if good > max(max_good, 4):
                 best_E, best_mask, max_good = E, mask.astype(np.uint8), good
-                niters = ransac_update_num_iters(prob, (n - good) / n, 5, niters)
+                if not exhaustive:
+                    niters = ransac_update_num_iters(prob, (n - good) / n, 5, niters)
                 trace["best_iter"], trace["best_model"] = it, mi
         it += 1
     trace["iters_run"] = it

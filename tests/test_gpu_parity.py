@@ -370,3 +370,36 @@ def test_extract_trajectory_from_a_frame_folder(env, tmp_path):
     assert np.allclose(np.linalg.norm(rows["absolute"][:, 4:8], axis=1), 1.0, atol=1e-9)      # unit quaternions
     with open(paths["absolute"]) as f:
         assert f.readline().endswith(" \n")      # the reference's trailing space (pose_estimation_module.py:80-86)
+
+
+# ----------------------------------------------------------------------------------------------- exhaustive RANSAC (configs[4])
+def test_exhaustive_ransac_matches_the_oracle_and_bounds_the_adaptive_result(env):
+    """ransac_exhaustive=1 scores every hypothesis (whole-GPU solve + Sampson sweep).  Against the numpy oracle run without
+    the adaptive stop (cv2 cannot be: it asserts prob < 1): same winner.  Size-independent properties at 20 000
+    correspondences: the exhaustive optimum is never worse than cv2's adaptive result, and it recovers the true inliers."""
+    from oracle import chain_np
+    n, iters = 1000, 1024
+    p1, p2, K, R, t, truth = env.synth.synthetic_correspondences(n, 0.4, 0.3, seed=4242)
+    ctx = env.native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=iters, ransac_exhaustive=True)
+    ctx.pose_points(p1, p2, K)
+    p = ctx.poses(0, 1)[0]
+    arr = ctx.pair_arrays(0, n)
+    ref = chain_np.pose_from_points(p1, p2, K, max_iters=iters, exhaustive=True)
+    assert p["status"] == 0 and p["ransac_iters"] == iters
+    assert abs(int(p["n_inliers"]) - int(ref["ransac_mask"].sum())) <= 2
+    assert mask_iou(arr["ransac_mask"], ref["ransac_mask"]) >= IOU_MIN
+    assert rot_err_deg(p["R"], ref["R"]) <= ROT_TOL_DEG and dir_err_deg(p["t"], ref["t"]) <= TDIR_TOL_DEG
+    ctx.close()
+    n = 20000
+    p1, p2, K, R, t, truth = env.synth.synthetic_correspondences(n, 0.4, 0.3, seed=n)
+    res = {}
+    for ex in (False, True):
+        ctx = env.native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=4096, ransac_exhaustive=ex)
+        ctx.pose_points(p1, p2, K)
+        res[ex] = (ctx.poses(0, 1)[0].copy(), ctx.pair_arrays(0, n)["ransac_mask"] > 0)
+        ctx.close()
+    assert res[True][0]["ransac_iters"] == 4096 and res[False][0]["ransac_iters"] < 4096
+    assert res[True][0]["n_inliers"] >= res[False][0]["n_inliers"]
+    got = res[True][1]
+    assert (got & truth).sum() / truth.sum() > 0.9 and (got & ~truth).sum() / max(1, got.sum()) < 0.05
+    assert rot_err_deg(res[True][0]["R"], R) < 0.5

@@ -43,4 +43,7 @@ for n in (1000, 5000, 20000, 50000):
     out["config4_ransac_%d_ms" % n] = round(timed(lambda: ctx.pose_points(a, b, K), 5), 3)
     out["config4_ransac_%d_iters" % n] = int(ctx.poses(0, 1)[0]["ransac_iters"])
     ctx.close()
+    ctx = _native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=4096, ransac_exhaustive=True)
+    out["config4_exhaustive4096_%d_ms" % n] = round(timed(lambda: ctx.pose_points(a, b, K), 5), 3)
+    ctx.close()
 print(json.dumps(out))
