@@ -603,7 +603,7 @@ struct BlockAcc {
 };
 
 constexpr int kSelectThreads = 1024;
-constexpr int kSelectSeqTail = 64;    // ranges this short are finished by one warp running the scalar replay
+constexpr int kSelectSeqTail = 32;    // ranges this short are finished by one warp running the scalar replay
 
 __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes, int level0) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
