@@ -303,8 +303,8 @@ def run_b200(a):
                   "inlier_ratio_median": float(np.median(host_poses["n_inliers"] / np.maximum(host_poses["n_matches"], 1)))}
 
     # ---- end to end through the public API: pinned host frames in, pose records out, every step
-    # (at most 10 steps' worth of distinct frames, copied device -> pinned host directly: 8 ranks share one host's RAM)
-    E_steps = min(K_steps, 10)
+    # (at most 20 steps' worth of distinct frames, copied device -> pinned host directly: 8 ranks share one host's RAM)
+    E_steps = min(K_steps, 20)
     src = frames[W_steps * B:(W_steps + E_steps) * B + 1]
     e2e_frames = torch.empty(src.shape, dtype=torch.uint8, pin_memory=True)
     e2e_frames.copy_(src)
