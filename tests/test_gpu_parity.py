@@ -403,3 +403,23 @@ def test_exhaustive_ransac_matches_the_oracle_and_bounds_the_adaptive_result(env
     got = res[True][1]
     assert (got & truth).sum() / truth.sum() > 0.9 and (got & ~truth).sum() / max(1, got.sum()) < 0.05
     assert rot_err_deg(res[True][0]["R"], R) < 0.5
+
+
+@pytest.mark.parametrize("size", [(67, 64), (4096, 96), (130, 1500), (1023, 769)])
+def test_image_stages_bit_exact_at_awkward_sizes(env, size):
+    """pyramid (smem window + DP2A path), FAST candidates and blur against the oracle at sizes that stress the tiling:
+    minimum size, maximum width, tall and narrow, nothing a multiple of 4."""
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    img[:, : w // 2] = np.clip(np.cumsum(rng.integers(-9, 10, (h, w // 2)), axis=1) + 128, 0, 255).astype(np.uint8)
+    ctx = env.native.Context(w, h, nfeatures=200, max_frames=2)
+    ctx.load_frames(img[None], 0)
+    ctx.orb(0, 1)
+    pyr = env.O.build_pyramid(img)
+    for L in range(8):
+        assert ctx.level_size(L)[:2] == (pyr[L].shape[1], pyr[L].shape[0])
+        assert np.array_equal(ctx.tap_image(0, L, 0), pyr[L]), ("pyramid", size, L)
+        assert np.array_equal(ctx.tap_image(0, L, 1), env.O.gaussian_blur_7x7(pyr[L])), ("blur", size, L)
+        assert np.array_equal(ctx.tap_candidates(0, L), env.O.fast_detect(pyr[L], 20, 31)), ("FAST", size, L)
+    ctx.close()
