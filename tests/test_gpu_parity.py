@@ -423,3 +423,29 @@ def test_image_stages_bit_exact_at_awkward_sizes(env, size):
         assert np.array_equal(ctx.tap_image(0, L, 1), env.O.gaussian_blur_7x7(pyr[L])), ("blur", size, L)
         assert np.array_equal(ctx.tap_candidates(0, L), env.O.fast_detect(pyr[L], 20, 31)), ("FAST", size, L)
     ctx.close()
+
+
+def test_trajectory_extraction_cli(env, tmp_path):
+    """dropin/trajectory_extraction.py (the ROS-free stand-in for trajectory_evaluation_dual_process.py's VO half), run as
+    a script on a folder of distorted frames with the reference's YAML schema: files written, one row per frame / pair."""
+    import subprocess
+    import sys
+    import os
+    from conftest import ROOT
+    n, w, h = 6, 640, 480
+    frames, _, K = env.synth.render_sequence(n, width=w, height=h, device="cuda", start_index=5)
+    fh = frames.cpu().numpy()
+    fdir = tmp_path / "frames"
+    fdir.mkdir()
+    for i in range(n):
+        np.save(fdir / ("%06d.npy" % i), fh[i])
+    calib = tmp_path / "calib.yaml"
+    calib.write_text("intrinsic_coeffs:\n- [%s]\ndistortion_coeffs:\n- [-0.2, 0.05, 0.0003, -0.0002, 0.0]\n" % ", ".join("%r" % float(v) for v in K.ravel()))
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "dropin", "trajectory_extraction.py"), str(fdir), str(calib), str(out),
+                        "--nfeatures", "500", "--batch", "3", "--undistort"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "pairs solved" in r.stdout
+    absolute = np.loadtxt(out / "stamped_traj_estimate_absolute.txt").reshape(-1, 8)
+    relative = np.loadtxt(out / "stamped_traj_estimate_relative.txt").reshape(-1, 8)
+    assert absolute.shape[0] == n and relative.shape[0] == n - 1 and (out / "stamped_traj_estimate_velocity.txt").exists()
