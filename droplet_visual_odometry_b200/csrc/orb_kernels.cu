@@ -696,15 +696,20 @@ __global__ void __launch_bounds__(256) k_angle_pack(OrbGeom g, OrbBuffers b, int
     const int u = lane - 15;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
+        // all 31 loads of the column are issued back to back (the whole 31x31 window is inside the level: keypoints keep a
+        // 31-px border), rows outside the disc are masked afterwards -- one memory latency per keypoint instead of fifteen
         const int au = abs(u);
         const uint8_t* c = img + (size_t)y * lv.pitch + x + u;
-        m10 = u * (int)c[0];
+        int vp[16], vm[16];
+        vp[0] = c[0];
+#pragma unroll
+        for (int v = 1; v <= 15; ++v) { vp[v] = c[v * lv.pitch]; vm[v] = c[-v * lv.pitch]; }
+        m10 = u * vp[0];
+#pragma unroll
         for (int v = 1; v <= 15; ++v) {
-            if (au <= c_umax[v]) {
-                int vp = c[v * lv.pitch], vm = c[-v * lv.pitch];
-                m10 += u * (vp + vm);
-                m01 += v * (vp - vm);
-            }
+            const int in = au <= c_umax[v] ? 1 : 0;
+            m10 += in * u * (vp[v] + vm[v]);
+            m01 += in * v * (vp[v] - vm[v]);
         }
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
