@@ -28,7 +28,7 @@ class dvo_config(ctypes.Structure):
                 ("fast_threshold", ctypes.c_int), ("max_frames", ctypes.c_int), ("matcher", ctypes.c_int),
                 ("ransac_max_iters", ctypes.c_int), ("ransac_prob", ctypes.c_double), ("ransac_threshold", ctypes.c_double),
                 ("distance_thresh", ctypes.c_double), ("ratio", ctypes.c_float), ("use_tma", ctypes.c_int), ("pipeline", ctypes.c_int),
-                ("ransac_exhaustive", ctypes.c_int)]
+                ("ransac_exhaustive", ctypes.c_int), ("nn_engine", ctypes.c_int)]
 
 
 class dvo_features(ctypes.Structure):
@@ -109,7 +109,7 @@ class Context:
 
     def __init__(self, width, height, nfeatures=500, nlevels=8, max_frames=2, matcher=DVO_MATCH_CROSSCHECK,
                  ransac_max_iters=1000, ransac_prob=0.999, ransac_threshold=1.0, distance_thresh=50.0, ratio=0.75,
-                 fast_threshold=20, device=0, use_tma=True, pipeline=True, ransac_exhaustive=False):
+                 fast_threshold=20, device=0, use_tma=True, pipeline=True, ransac_exhaustive=False, nn_engine=0):
         self.lib = load_library()
         self.torch = _torch()
         cfg = dvo_config()
@@ -120,6 +120,7 @@ class Context:
         cfg.ratio, cfg.fast_threshold, cfg.use_tma = float(ratio), int(fast_threshold), int(bool(use_tma))
         cfg.pipeline = int(bool(pipeline))
         cfg.ransac_exhaustive = int(bool(ransac_exhaustive))
+        cfg.nn_engine = int(nn_engine)
         self.cfg = cfg
         self.device = int(device)
         self.width, self.height, self.nlevels = int(width), int(height), int(nlevels)

@@ -239,7 +239,7 @@ void dvo_default_config(dvo_config* c) {
     c->max_frames = 2;
     c->matcher = DVO_MATCH_CROSSCHECK;
     c->ransac_max_iters = 1000; c->ransac_prob = 0.999; c->ransac_threshold = 1.0;
-    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1; c->pipeline = 1; c->ransac_exhaustive = 0;
+    c->distance_thresh = 50.0; c->ratio = 0.75f; c->use_tma = 1; c->pipeline = 1; c->ransac_exhaustive = 0; c->nn_engine = 0;
 }
 
 int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
@@ -305,6 +305,9 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     pg.matcher = cfg->matcher;
     pg.maxIters = cfg->ransac_max_iters;
     pg.exhaustive = cfg->ransac_exhaustive != 0;
+    pg.nnTensor = cfg->nn_engine == 0 && cfg->matcher == DVO_MATCH_CROSSCHECK;
+    pg.numSms = 148;
+    cudaDeviceGetAttribute(&pg.numSms, cudaDevAttrMultiProcessorCount, ctx->device);
     pg.prob = cfg->ransac_prob;
     pg.threshold = cfg->ransac_threshold;
     pg.distThresh = cfg->distance_thresh;
@@ -313,6 +316,12 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     DA(pb.nnIdx, P * 2 * M);
     DA(pb.nnDist, P * 2 * M);
     DA(pb.nn2Dist, P * M);
+    pb.descX = nullptr;
+    pb.descXRows = nn_tensor_rows(g.maxkp);
+    if (pg.nnTensor) {
+        DA(pb.descX, (P + 1) * (size_t)pb.descXRows * 256);
+        nn_tensor_init();
+    }
     DA(pb.matches, P * M * 3);
     DA(pb.matchCount, P);
     DA(pb.ptsPrev, P * M * 2);

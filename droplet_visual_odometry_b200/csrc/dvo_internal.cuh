@@ -90,6 +90,8 @@ struct PairGeom {
     int matcher;          // 0 crosscheck, 1 knn ratio + reverse check
     int maxIters;
     int exhaustive;       // score all maxIters hypotheses (no adaptive stop)
+    int nnTensor;         // cross-check matcher on the tensor cores (nn_tensor.cu) instead of XOR+POPC
+    int numSms;
     int rngCount;         // entries of PairBuffers::rngStates
     double prob, threshold, distThresh;
     float ratio;
@@ -103,6 +105,8 @@ struct PairBuffers {
     int* nnIdx;           // [pairs][2 dirs][maxkp]      best index
     int* nnDist;          // [pairs][2][maxkp]
     int* nn2Dist;         // [pairs][maxkp]              second-best distance (forward only, knn mode)
+    int8_t* descX;        // [pairs + 1][descXRows][256] descriptors of one dvo_pairs call as +-1 bytes (tensor-core matcher)
+    int descXRows;        // maxkp rounded up to the matcher's column tile
     int* matches;         // [pairs][maxkp][3]           (queryIdx, trainIdx, distance) sorted by (distance, queryIdx)
     int* matchCount;      // [pairs]
     float* ptsPrev;       // [pairs][maxkp][2]
@@ -164,6 +168,10 @@ void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& i
                    size_t frameStride, int slot0, cudaStream_t st);
 void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_src, int n, size_t pitch, size_t frameStride,
                         int slot0, cudaStream_t st);
+int nn_tensor_rows(int maxkp);
+void nn_tensor_init();
+void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+                      int nPairs, int numSms, cudaStream_t st);
 void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
                   int pair0, int nPairs, const double* K, cudaStream_t st);
 

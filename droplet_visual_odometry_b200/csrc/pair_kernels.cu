@@ -815,9 +815,11 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
     const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
     {
         ProfScope ps_(PF_NN, st);
-        cudaMemsetAsync(pb.nnIdx + (size_t)pair0 * 2 * pg.maxkp, 0xFF, sizeof(int) * 2 * (size_t)nPairs * pg.maxkp, st);
         const int qBlocks = (pg.maxkp + 127) / 128;
-        if (pg.matcher == DVO_MATCH_CROSSCHECK) {
+        if (pg.nnTensor) {
+            launch_nn_tensor(og, ob, pg, pb, slotA0, pair0, nPairs, pg.numSms, st);      // writes every row key itself
+        } else if (cudaMemsetAsync(pb.nnIdx + (size_t)pair0 * 2 * pg.maxkp, 0xFF, sizeof(int) * 2 * (size_t)nPairs * pg.maxkp, st),
+                   pg.matcher == DVO_MATCH_CROSSCHECK) {
             const int nSplit = qBlocks >= 4 ? 4 : 1;
             k_nn<true><<<dim3(qBlocks, nSplit, nPairs), 128, 0, st>>>(og, ob, pg, pb, slotA0, pair0);
         } else {

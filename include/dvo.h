@@ -61,6 +61,8 @@ typedef struct dvo_config {
     int ransac_exhaustive;   /* 0 (default): cv.findEssentialMat's adaptive stop.  1: every one of ransac_max_iters hypotheses
                                 is solved and scored (whole-GPU batched solve + Sampson sweep; BASELINE configs[4] "all
                                 hypotheses scored"); the first model with the highest inlier count wins                */
+    int nn_engine;           /* cross-check matcher: 0 (default) int8 tensor-core GEMM (tcgen05, 256 - 2*hamming = dot of +-1 bytes);
+                                1: XOR + POPC kernel.  Both give cv2's matches bit for bit.  The ratio matcher always uses 1 */
 } dvo_config;
 
 /* Result of one frame pair: what cv.findEssentialMat + cv.recoverPose return (visual_odometry_v3.py:297-306). */

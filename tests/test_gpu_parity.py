@@ -449,3 +449,57 @@ def test_trajectory_extraction_cli(env, tmp_path):
     absolute = np.loadtxt(out / "stamped_traj_estimate_absolute.txt").reshape(-1, 8)
     relative = np.loadtxt(out / "stamped_traj_estimate_relative.txt").reshape(-1, 8)
     assert absolute.shape[0] == n and relative.shape[0] == n - 1 and (out / "stamped_traj_estimate_velocity.txt").exists()
+
+
+# ----------------------------------------------------------------------------------------------- tensor-core matcher
+def _bf_crosscheck_numpy(da, db):
+    """cv.BFMatcher(NORM_HAMMING, crossCheck=True).match + sorted(key=distance) restated with numpy (ties -> lowest index)."""
+    lut = np.array([bin(i).count("1") for i in range(256)], dtype=np.int32)
+    d = lut[da[:, None, :] ^ db[None, :, :]].sum(axis=2)
+    fwd, bwd = d.argmin(axis=1), d.argmin(axis=0)
+    m = [(int(d[i, fwd[i]]), i, int(fwd[i])) for i in range(len(da)) if bwd[fwd[i]] == i]
+    m.sort()
+    return np.array([(i, j, dist) for dist, i, j in m], dtype=np.int32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("na,nb", [(700, 515), (1, 300), (300, 1), (129, 257), (2000, 2000), (37, 37)])
+def test_tensor_core_matcher_equals_popc_matcher_and_numpy(env, na, nb):
+    """nn_engine 0 (int8 tcgen05 GEMM) and nn_engine 1 (XOR+POPC) on caller descriptors built to tie often: few distinct bit
+    patterns, so the lowest-index rule decides many rows and columns; ragged counts exercise the masked column tiles."""
+    rng = np.random.default_rng(na * 7919 + nb)
+    base = rng.integers(0, 256, size=(24, 32), dtype=np.uint8)
+
+    def make(n):
+        d = base[rng.integers(0, len(base), size=n)].copy()
+        flips = rng.integers(0, 3, size=n)
+        for r in range(n):
+            for _ in range(flips[r]):
+                d[r, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8))
+        return d
+    da, db = make(na), make(nb)
+    pa = rng.uniform(40, 1200, size=(na, 2)).astype(np.float32)
+    pb = rng.uniform(40, 1000, size=(nb, 2)).astype(np.float32)
+    ref = _bf_crosscheck_numpy(da, db)
+    got = []
+    for engine in (0, 1):
+        ctx = env.native.Context(1280, 1024, nfeatures=2000, max_frames=2, nn_engine=engine)
+        ctx.set_features(0, pa, da); ctx.set_features(1, pb, db)
+        ctx.pairs(0, 0, 1, env.K)
+        p = ctx.poses(0, 1)[0]
+        got.append(ctx.pair_arrays(0, p["n_matches"])["matches"])
+        ctx.close()
+    assert np.array_equal(got[1], ref), "POPC matcher differs from numpy"
+    assert np.array_equal(got[0], ref), "tensor-core matcher differs from numpy"
+
+
+def test_tensor_core_matcher_on_real_features_many_pairs(env):
+    """Same frames through both engines with 4 pairs in one call (persistent work list spans pairs and directions)."""
+    out = []
+    for engine in (0, 1):
+        ctx = env.native.Context(1280, 1024, nfeatures=2000, max_frames=5, nn_engine=engine)
+        ctx.load_frames(env.frames, 0); ctx.orb(0, 5); ctx.pairs(0, 0, 4, env.K)
+        ps = ctx.poses(0, 4)
+        out.append([ctx.pair_arrays(i, ps[i]["n_matches"])["matches"] for i in range(4)])
+        ctx.close()
+    for i in range(4):
+        assert len(out[0][i]) > 100 and np.array_equal(out[0][i], out[1][i])
