@@ -14,8 +14,9 @@
 //                   direction (train -> query) is simply the transposed product, scheduled as its own work items.
 //       warp 4      one lane issues tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, eight per tile) into a double-buffered
 //                   TMEM accumulator (2 x 256 columns) and commits to the mbarriers that free the operand stages
-//       warps 5-8   producers: cp.async 16-byte pieces straight into the canonical no-swizzle K-major core-matrix layout
-//                   (8 rows x 16 B contiguous; K-adjacent core matrices 128 B apart, 8-row groups 2 KB apart)
+//       warp 5      producer: one lane streams the operand tiles with cp.async.bulk (mbarrier complete_tx).  k_expand_desc
+//                   already stores the rows in the canonical no-swizzle K-major core-matrix order (8 rows x 16 B
+//                   contiguous; K-adjacent core matrices 128 B apart, 8-row groups 2 KB apart): a tile is one block
 //   A work item is (pair, direction, 128-row block); it streams every 256-column tile of the other frame past its rows.
 #include "dvo_internal.cuh"
 
@@ -27,10 +28,10 @@ constexpr int kRowBytes = 256;                 // one expanded descriptor
 constexpr int kTileM = 128, kTileN = 256;
 constexpr int kABytes = kTileM * kRowBytes;    // 32 KB
 constexpr int kBBytes = kTileN * kRowBytes;    // 64 KB
-constexpr int kAStages = 2, kBStages = 2, kAccStages = 2;
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 288
-constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kAStages = 2, kBStages = 2;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (kEpiWarps + 2) * 32;                  // epilogue, MMA warp, producer warp
+constexpr int kBulkBytes = 16384;              // one cp.async.bulk
 constexpr uint32_t kLbo = 128, kSbo = 2048;    // bytes: K-adjacent core matrices / 8-row groups
 constexpr size_t kSmemBytes = (size_t)kAStages * kABytes + (size_t)kBStages * kBBytes + 1024 /*alignment slack*/ + 256;
 
@@ -45,6 +46,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
 }
 // Bounded spin: a protocol error traps (the launch fails loudly) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -138,14 +147,17 @@ __device__ __forceinline__ Item decode_item(int item, int mTiles, const int* fea
 
 }  // namespace
 
-// bits -> bytes: bit clear -> 0x01 (+1), bit set -> 0xFF (-1).  One thread per 16 output bytes.
+// bits -> bytes: bit clear -> 0x01 (+1), bit set -> 0xFF (-1).  One thread per 16 output bytes, written in the order the
+// MMA's no-swizzle K-major descriptor reads them: [8-row group][16-byte K chunk][row in group][16 B], so that a tile of
+// 128 or 256 rows is one contiguous block for cp.async.bulk.
 __global__ void __launch_bounds__(256) k_expand_desc(OrbGeom og, OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int nSlots) {
     const size_t id = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const int chunk = (int)(id & 15);
-    const size_t rowId = id >> 4;
-    const int ls = (int)(rowId / pg.maxkp), r = (int)(rowId - (size_t)ls * pg.maxkp);
+    const int r8 = (int)(id & 7), chunk = (int)((id >> 3) & 15);
+    const size_t grpId = id >> 7;
+    const int groups = pb.descXRows >> 3;
+    const int ls = (int)(grpId / groups), g = (int)(grpId - (size_t)ls * groups);
     if (ls >= nSlots) return;
-    const int slot = slotA0 + ls;
+    const int slot = slotA0 + ls, r = g * 8 + r8;
     if (r >= min(ob.featCount[slot], pg.maxkp)) return;
     const uint32_t bits = reinterpret_cast<const uint16_t*>(ob.featDesc + ((size_t)slot * og.maxkp + r) * 32)[chunk];
     uint32_t w[4];
@@ -155,7 +167,8 @@ __global__ void __launch_bounds__(256) k_expand_desc(OrbGeom og, OrbBuffers ob, 
         const uint32_t ones = (nib * 0x00204081u) & 0x01010101u;     // bit k of the nibble -> byte k
         w[q] = (ones * 0xFFu) | 0x01010101u;
     }
-    reinterpret_cast<uint4*>(pb.descX + ((size_t)ls * pb.descXRows + r) * kRowBytes)[chunk] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(pb.descX + (size_t)ls * pb.descXRows * kRowBytes)[(size_t)g * 128 + chunk * 8 + r8] =
+        make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -171,9 +184,9 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(fullA + 8 * s, kProdThreads);
+            mbar_init(fullA + 8 * s, 1);
             mbar_init(emptyA + 8 * s, 1);
-            mbar_init(fullB + 8 * s, kProdThreads);
+            mbar_init(fullB + 8 * s, 1);
             mbar_init(emptyB + 8 * s, 1);
             mbar_init(accFull + 8 * s, 1);
             mbar_init(accEmpty + 8 * s, kEpiWarps * 32);
@@ -252,7 +265,6 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
                     const uint32_t bs = bUse & 1, cs = accUse & 1;
                     mbar_wait(fullB + 8 * bs, (bUse >> 1) & 1);
                     mbar_wait(accEmpty + 8 * cs, ((accUse >> 1) & 1) ^ 1);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d = tmemBase + cs * kTileN;
 #pragma unroll
@@ -267,48 +279,32 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
         }
         __syncwarp();
     } else {
-        // ---------------------------------------------------------------- producers
-        const int pt = threadIdx.x - (kEpiWarps + 1) * 32;        // 0..127
-        const int r8 = pt & 7, cq = (pt >> 3) & 3, grp = pt >> 5;  // row in group, chunk quarter, warp
-        uint32_t aUse = 0, bUse = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x) {
-            const Item it = decode_item(item, mTiles, ob.featCount, slotA0, pg.maxkp);
-            if (!it.work) continue;
-            {
-                const uint32_t as = aUse & 1;
-                mbar_wait(emptyA + 8 * as, ((aUse >> 1) & 1) ^ 1);
-                const int8_t* src = pb.descX + (size_t)it.slotX * slotStride + (size_t)it.mt * kTileM * kRowBytes;
-                const uint32_t dst = sA + as * kABytes;
-                // 16 row groups x 4 chunk quads = 64 (group, quad) units, 32 lanes each; 4 warps -> 16 units per warp
-#pragma unroll 4
-                for (int u = grp; u < (kTileM / 8) * 4; u += kProdWarps) {
-                    const int g = u >> 2, c = (u & 3) * 4 + cq;
-                    const int row = g * 8 + r8;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + g * kSbo + c * kLbo + r8 * 16),
-                                 "l"(src + (size_t)row * kRowBytes + c * 16)
-                                 : "memory");
+        // ---------------------------------------------------------------- producer (one lane): bulk copies
+        // k_expand_desc stores the descriptors in the core-matrix order the MMA reads, so a tile is one contiguous block
+        if (lane == 0) {
+            uint32_t aUse = 0, bUse = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const Item it = decode_item(item, mTiles, ob.featCount, slotA0, pg.maxkp);
+                if (!it.work) continue;
+                {
+                    const uint32_t as = aUse & 1;
+                    mbar_wait(emptyA + 8 * as, ((aUse >> 1) & 1) ^ 1);
+                    mbar_expect_tx(fullA + 8 * as, kABytes);
+                    const int8_t* src = pb.descX + (size_t)it.slotX * slotStride + (size_t)it.mt * kABytes;
+                    for (int q = 0; q < kABytes; q += kBulkBytes) bulk_load(sA + as * kABytes + q, src + q, kBulkBytes, fullA + 8 * as);
+                    ++aUse;
                 }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fullA + 8 * as) : "memory");
-                ++aUse;
-            }
-            const int nTiles = (it.nY + kTileN - 1) / kTileN;
-            for (int nt = 0; nt < nTiles; ++nt, ++bUse) {
-                const uint32_t bs = bUse & 1;
-                mbar_wait(emptyB + 8 * bs, ((bUse >> 1) & 1) ^ 1);
-                const int8_t* src = pb.descX + (size_t)it.slotY * slotStride + (size_t)nt * kTileN * kRowBytes;
-                const uint32_t dst = sB + bs * kBBytes;
-#pragma unroll 4
-                for (int u = grp; u < (kTileN / 8) * 4; u += kProdWarps) {
-                    const int g = u >> 2, c = (u & 3) * 4 + cq;
-                    const int row = g * 8 + r8;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + g * kSbo + c * kLbo + r8 * 16),
-                                 "l"(src + (size_t)row * kRowBytes + c * 16)
-                                 : "memory");
+                const int nTiles = (it.nY + kTileN - 1) / kTileN;
+                for (int nt = 0; nt < nTiles; ++nt, ++bUse) {
+                    const uint32_t bs = bUse & 1;
+                    mbar_wait(emptyB + 8 * bs, ((bUse >> 1) & 1) ^ 1);
+                    mbar_expect_tx(fullB + 8 * bs, kBBytes);
+                    const int8_t* src = pb.descX + (size_t)it.slotY * slotStride + (size_t)nt * kBBytes;
+                    for (int q = 0; q < kBBytes; q += kBulkBytes) bulk_load(sB + bs * kBBytes + q, src + q, kBulkBytes, fullB + 8 * bs);
                 }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fullB + 8 * bs) : "memory");
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -326,7 +322,7 @@ void nn_tensor_init() {
 void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
                       int nPairs, int numSms, cudaStream_t st) {
     const int nSlots = nPairs + 1;
-    const size_t pieces = (size_t)nSlots * pg.maxkp * 16;
+    const size_t pieces = (size_t)nSlots * pb.descXRows * 16;
     k_expand_desc<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(og, ob, pg, pb, slotA0, nSlots);
     const int mTiles = (pg.maxkp + kTileM - 1) / kTileM;
     const int total = nPairs * 2 * mTiles;
