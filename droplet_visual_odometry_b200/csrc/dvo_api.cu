@@ -305,7 +305,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     pg.matcher = cfg->matcher;
     pg.maxIters = cfg->ransac_max_iters;
     pg.exhaustive = cfg->ransac_exhaustive != 0;
-    pg.nnTensor = cfg->nn_engine == 0 && cfg->matcher == DVO_MATCH_CROSSCHECK;
+    pg.nnTensor = cfg->nn_engine == 0;
     pg.numSms = 148;
     cudaDeviceGetAttribute(&pg.numSms, cudaDevAttrMultiProcessorCount, ctx->device);
     pg.prob = cfg->ransac_prob;

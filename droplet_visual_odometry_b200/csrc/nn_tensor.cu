@@ -126,6 +126,21 @@ __device__ __forceinline__ int chunk_min(const int (&v)[32], int negScale, int l
     return m;
 }
 
+// Two smallest keys of the chunk (ratio matcher: knnMatch(k=2)); different columns have different keys, so the pair is
+// the two nearest neighbours in cv2's tie order.
+template <bool kMasked>
+__device__ __forceinline__ void chunk_min2(const int (&v)[32], int negScale, int lim, int& m1, int& m2) {
+    m1 = 0x7fffffff; m2 = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        int k = v[c] * negScale + ((256 << 15) + c);
+        if (kMasked && c >= lim) k = 0x7fffffff;
+        const int t = max(m1, k);
+        m1 = min(m1, k);
+        m2 = min(m2, t);
+    }
+}
+
 struct Item { int pair, dir, mt, nX, nY, slotX, slotY; bool rows, work; };
 
 __device__ __forceinline__ Item decode_item(int item, int mTiles, const int* featCount, int slotA0, int maxkp) {
@@ -171,6 +186,7 @@ __global__ void __launch_bounds__(256) k_expand_desc(OrbGeom og, OrbBuffers ob, 
         make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+template <bool kSecond>      // kSecond: forward rows also keep the runner-up distance (ratio matcher)
 __global__ void __launch_bounds__(kThreads, 1)
 k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, int nPairs, int mTiles, int negScale) {
     extern __shared__ uint8_t smemRaw[];
@@ -214,7 +230,21 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
             const Item it = decode_item(item, mTiles, ob.featCount, slotA0, pg.maxkp);
             if (!it.rows) continue;
             const int row = it.mt * kTileM + threadIdx.x;
-            int best = 0x7fffffff;
+            int best = 0x7fffffff, second = 0x7fffffff;
+            const bool two = kSecond && it.dir == 0;
+            auto consume = [&](const int (&v)[32], int lim, int colBase) {
+                if (lim <= 0) return;
+                if (two) {
+                    int a1, a2;
+                    if (lim >= 32) chunk_min2<false>(v, negScale, 32, a1, a2); else chunk_min2<true>(v, negScale, lim, a1, a2);
+                    a1 += colBase;                                   // a chunk always has its first column: a1 is a real key
+                    if (a2 != 0x7fffffff) a2 += colBase;
+                    second = min(max(best, a1), min(second, a2));
+                    best = min(best, a1);
+                } else {
+                    best = min(best, (lim >= 32 ? chunk_min<false>(v, negScale, 32) : chunk_min<true>(v, negScale, lim)) + colBase);
+                }
+            };
             if (it.work) {
                 const int nTiles = (it.nY + kTileN - 1) / kTileN;
                 for (int nt = 0; nt < nTiles; ++nt, ++accUse) {
@@ -230,26 +260,25 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
                     for (int k = 0; k < kTileN / 32; k += 2) {
                         tmem_ld_wait(va);
                         tmem_ld32(taddr + (k + 1) * 32, vb);
-                        {
-                            const int lim = valid - k * 32;
-                            if (lim >= 32) best = min(best, chunk_min<false>(va, negScale, 32) + col0 + k * 32);
-                            else if (lim > 0) best = min(best, chunk_min<true>(va, negScale, lim) + col0 + k * 32);
-                        }
+                        consume(va, valid - k * 32, col0 + k * 32);
                         tmem_ld_wait(vb);
                         if (k + 2 < kTileN / 32) tmem_ld32(taddr + (k + 2) * 32, va);
-                        {
-                            const int lim = valid - (k + 1) * 32;
-                            if (lim >= 32) best = min(best, chunk_min<false>(vb, negScale, 32) + col0 + (k + 1) * 32);
-                            else if (lim > 0) best = min(best, chunk_min<true>(vb, negScale, lim) + col0 + (k + 1) * 32);
-                        }
+                        consume(vb, valid - (k + 1) * 32, col0 + (k + 1) * 32);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(accEmpty + 8 * cs);
                 }
             }
-            if (row < it.nX)
-                reinterpret_cast<uint32_t*>(pb.nnIdx)[((size_t)(pair0 + it.pair) * 2 + it.dir) * pg.maxkp + row] =
-                    best == 0x7fffffff ? 0xFFFFFFFFu : (uint32_t)best;
+            if (row < it.nX) {
+                const size_t o = ((size_t)(pair0 + it.pair) * 2 + it.dir) * pg.maxkp + row;
+                if (two) {            // k_match_sort's ratio path: plain index, distance, runner-up distance
+                    pb.nnIdx[o] = best == 0x7fffffff ? -1 : (best & 0xFFFF);
+                    pb.nnDist[o] = best == 0x7fffffff ? 0x7fffffff : (best >> 16);
+                    pb.nn2Dist[(size_t)(pair0 + it.pair) * pg.maxkp + row] = second == 0x7fffffff ? 0x7fffffff : (second >> 16);
+                } else {
+                    reinterpret_cast<uint32_t*>(pb.nnIdx)[o] = best == 0x7fffffff ? 0xFFFFFFFFu : (uint32_t)best;
+                }
+            }
         }
     } else if (warp == kEpiWarps) {
         // ---------------------------------------------------------------- MMA issue (one lane)
@@ -316,7 +345,8 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
 int nn_tensor_rows(int maxkp) { return ((maxkp + kTileN - 1) / kTileN) * kTileN; }
 
 void nn_tensor_init() {
-    cudaFuncSetAttribute(k_nn_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaFuncSetAttribute(k_nn_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaFuncSetAttribute(k_nn_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 }
 
 void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
@@ -326,7 +356,10 @@ void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& p
     k_expand_desc<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(og, ob, pg, pb, slotA0, nSlots);
     const int mTiles = (pg.maxkp + kTileM - 1) / kTileM;
     const int total = nPairs * 2 * mTiles;
-    k_nn_tensor<<<std::min(total, numSms), kThreads, kSmemBytes, st>>>(ob, pg, pb, slotA0, pair0, nPairs, mTiles, -32768);
+    if (pg.matcher == DVO_MATCH_KNN_RATIO)
+        k_nn_tensor<true><<<std::min(total, numSms), kThreads, kSmemBytes, st>>>(ob, pg, pb, slotA0, pair0, nPairs, mTiles, -32768);
+    else
+        k_nn_tensor<false><<<std::min(total, numSms), kThreads, kSmemBytes, st>>>(ob, pg, pb, slotA0, pair0, nPairs, mTiles, -32768);
 }
 
 }  // namespace dvo

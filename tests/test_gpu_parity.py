@@ -503,3 +503,33 @@ def test_tensor_core_matcher_on_real_features_many_pairs(env):
         ctx.close()
     for i in range(4):
         assert len(out[0][i]) > 100 and np.array_equal(out[0][i], out[1][i])
+
+
+@pytest.mark.parametrize("na,nb", [(700, 515), (300, 1), (129, 257), (1500, 2000)])
+def test_tensor_core_ratio_matcher_equals_popc_ratio_matcher(env, na, nb):
+    """knnMatch(k=2) + ratio + reverse check: the runner-up distance kept by the tensor-core epilogue gives the same match
+    list as the XOR+POPC kernel (which test_config4 pins to cv2), on descriptors with many equal distances."""
+    rng = np.random.default_rng(na * 104729 + nb)
+    base = rng.integers(0, 256, size=(40, 32), dtype=np.uint8)
+
+    def make(n):
+        d = base[rng.integers(0, len(base), size=n)].copy()
+        for r in range(n):
+            for _ in range(rng.integers(0, 12)):
+                d[r, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8))
+        return d
+    da, db = make(na), make(nb)
+    pa = rng.uniform(40, 1200, size=(na, 2)).astype(np.float32)
+    pb = rng.uniform(40, 1000, size=(nb, 2)).astype(np.float32)
+    got = []
+    for engine in (0, 1):
+        ctx = env.native.Context(1280, 1024, nfeatures=2000, max_frames=2, nn_engine=engine,
+                                 matcher=env.native.DVO_MATCH_KNN_RATIO)
+        ctx.set_features(0, pa, da); ctx.set_features(1, pb, db)
+        ctx.pairs(0, 0, 1, env.K)
+        p = ctx.poses(0, 1)[0]
+        got.append((int(p["n_matches"]), ctx.pair_arrays(0, p["n_matches"])["matches"]))
+        ctx.close()
+    assert got[0][0] == got[1][0] and np.array_equal(got[0][1], got[1][1])
+    if nb >= 2 and na > 100:
+        assert got[0][0] > 0
