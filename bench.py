@@ -343,7 +343,7 @@ def run_b200(a):
         total_px = sum(px)
         pyr_bytes = sum(px[L - 1] + px[L] for L in range(1, len(px)))
         alg_bytes_per_frame = {"k_pyr_down": pyr_bytes, "k_fast_nms": total_px, "k_blur": 2 * total_px,
-                               "k_ingest": px[0] * ((3 if a.ingest == "bgr" else 1) + 1)}
+                               "k_load_or_ingest": px[0] * ((3 if a.ingest == "bgr" else 1) + 1)}
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         peaks = {}
         try:

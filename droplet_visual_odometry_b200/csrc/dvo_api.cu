@@ -878,7 +878,7 @@ int dvo_profile_collect(double* ms, int* count, int n) {
 }
 const char* dvo_profile_name(int id) {
     static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_compact", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
-                                          "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final", "k_ingest"};
+                                          "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final", "k_load_or_ingest"};
     return (id >= 0 && id < PF_COUNT) ? names[id] : "";
 }
 
