@@ -365,11 +365,14 @@ def run_b200(a):
                 st["achieved_GBps"] = round(bytes_total / (tms * 1e-3) / 1e9, 2)
                 st["frac_of_hbm_peak"] = round(st["achieved_GBps"] / peak, 4)
             if name == "k_nn":
-                # every distance is computed once (row and column minima from the same popcounts): N*N*8 POPC32 per pair
-                st["gpopc_per_s"] = round(nkp * nkp * 8 * B * cnt / (tms * 1e-3) / 1e9, 1)
-                # algorithmic POPC32 rate (8 per distance) against the nominal XU pipe rate, 16 POPC/clk/SM; the kernel executes
-                # 6 POPC per distance (two carry-save adders), so this can exceed 1
-                st["frac_of_popc_peak"] = round(st["gpopc_per_s"] * 1e9 / (148 * 16 * 1.965e9), 4)
+                # cross-check matcher = int8 GEMM on the tensor cores (k_expand_desc + k_nn_tensor): both directions of the
+                # N x N x 256 distance matrix, 2 ops per multiply-add; peak = 2 x the measured bf16 rate (int8 runs at twice
+                # bf16 on sm_100a), else 2 x 2250 nominal
+                ops = 2.0 * 2 * nkp * nkp * 256 * B * cnt
+                st["int8_tops"] = round(ops / (tms * 1e-3) / 1e12, 1)
+                int8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
+                st["frac_of_int8_tensor_peak"] = round(st["int8_tops"] / int8_peak, 4)
+                st["int8_peak_tops"] = int8_peak
             stages[name] = st
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         dms, dcnt = prof[dom]

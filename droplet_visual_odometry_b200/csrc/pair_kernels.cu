@@ -827,7 +827,7 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
         }
     }
     { ProfScope ps_(PF_SORT, st); k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy); }
-    g_pair_launches += 2;
+    g_pair_launches += pg.nnTensor ? 3 : 2;      // (k_expand_desc + k_nn_tensor | k_nn) + k_match_sort
     debug_sync("k_nn+sort", st);
     launch_ransac_pose(og, ob, pg, pb, slotA0, pair0, nPairs, K, st);
 }
