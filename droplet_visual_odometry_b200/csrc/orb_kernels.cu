@@ -797,29 +797,36 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, OrbBuffers b, int slot0
         row_quad(p, ry, gx - x0);
     }
     __syncthreads();
-    // column pass, 4 pixels per thread
-    for (int i = tid; i < kTileH * (kTileW / 4); i += 256) {
-        const int r = i / (kTileW / 4), xq = (i - r * (kTileW / 4)) * 4;
-        const int y = y0 + r, x = x0 + xq;
-        if (y >= lv.h || x >= lv.w) continue;
-        const float* h = hrow + (r + 3) * kTileW + xq;
-        const float4 c = *reinterpret_cast<const float4*>(h);
-        const float4 u1 = *reinterpret_cast<const float4*>(h - kTileW), d1 = *reinterpret_cast<const float4*>(h + kTileW);
-        const float4 u2 = *reinterpret_cast<const float4*>(h - 2 * kTileW), d2 = *reinterpret_cast<const float4*>(h + 2 * kTileW);
-        const float4 u3 = *reinterpret_cast<const float4*>(h - 3 * kTileW), d3 = *reinterpret_cast<const float4*>(h + 3 * kTileW);
-        uint32_t word = 0;
+    // column pass: a warp owns four output rows of the tile, a lane four adjacent columns; the ten row-pass rows those
+    // outputs need are read once into registers (10 LDS.128 for 16 pixels instead of 7 per 4)
+    static_assert(kTileW == 128 && kTileH == 32, "column pass layout: 32 lanes x 4 columns, 8 warps x 4 rows");
+    {
+        const int xq = (tid & 31) * 4, r0 = (tid >> 5) * 4;
+        const int x = x0 + xq;
+        if (x < lv.w && y0 + r0 < lv.h) {
+            float4 w[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) w[j] = *reinterpret_cast<const float4*>(hrow + (r0 + j) * kTileW + xq);
+            uint8_t* op = out + (size_t)(y0 + r0) * lv.pitch + x;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                if (y0 + r0 + rr >= lv.h) break;
+                const float4 c = w[rr + 3], u1 = w[rr + 2], d1 = w[rr + 4], u2 = w[rr + 1], d2 = w[rr + 5], u3 = w[rr], d3 = w[rr + 6];
+                uint32_t word = 0;
 #define DVO_BLUR_COL(F, SH)                                        \
-        {                                                          \
-            float s = fmul(k3, c.F);                               \
-            s = ffma(k2, fadd(d1.F, u1.F), s);                     \
-            s = ffma(k1, fadd(d2.F, u2.F), s);                     \
-            s = ffma(k0, fadd(d3.F, u3.F), s);                     \
-            /* 0 <= s <= 255 * (sum of weights)^2 < 255.5: no saturation needed */ \
-            word |= (uint32_t)__float2int_rn(s) << SH;             \
-        }
-        DVO_BLUR_COL(x, 0) DVO_BLUR_COL(y, 8) DVO_BLUR_COL(z, 16) DVO_BLUR_COL(w, 24)
+                {                                                  \
+                    float s = fmul(k3, c.F);                       \
+                    s = ffma(k2, fadd(d1.F, u1.F), s);             \
+                    s = ffma(k1, fadd(d2.F, u2.F), s);             \
+                    s = ffma(k0, fadd(d3.F, u3.F), s);             \
+                    /* 0 <= s <= 255 * (sum of weights)^2 < 255.5: no saturation needed */ \
+                    word |= (uint32_t)__float2int_rn(s) << SH;     \
+                }
+                DVO_BLUR_COL(x, 0) DVO_BLUR_COL(y, 8) DVO_BLUR_COL(z, 16) DVO_BLUR_COL(w, 24)
 #undef DVO_BLUR_COL
-        *reinterpret_cast<uint32_t*>(out + (size_t)y * lv.pitch + x) = word;
+                *reinterpret_cast<uint32_t*>(op + (size_t)rr * lv.pitch) = word;
+            }
+        }
     }
 }
 
