@@ -29,7 +29,8 @@ constexpr int kTileM = 128, kTileN = 256;
 constexpr int kABytes = kTileM * kRowBytes;    // 32 KB
 constexpr int kBBytes = kTileN * kRowBytes;    // 64 KB
 constexpr int kAStages = 2, kBStages = 2;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;                   // two warps per TMEM lane quarter, each takes half of a tile's columns
+constexpr int kEpiCols = kTileN / (kEpiWarps / 4);
 constexpr int kThreads = (kEpiWarps + 2) * 32;                  // epilogue, MMA warp, producer warp
 constexpr int kBulkBytes = 16384;              // one cp.async.bulk
 constexpr uint32_t kLbo = 128, kSbo = 2048;    // bytes: K-adjacent core matrices / 8-row groups
@@ -141,6 +142,39 @@ __device__ __forceinline__ void chunk_min2(const int (&v)[32], int negScale, int
     }
 }
 
+// One 32-column chunk into the running row minimum (and runner-up).  lim = valid columns left at the chunk's start.
+template <bool kTwo>
+__device__ __forceinline__ void epi_chunk(const int (&v)[32], int lim, int colBase, int negScale, int& best, int& second) {
+    if (!kTwo) {
+        if (lim >= 32) best = min(best, chunk_min<false>(v, negScale, 32) + colBase);
+        else if (lim > 0) best = min(best, chunk_min<true>(v, negScale, lim) + colBase);
+    } else if (lim > 0) {
+        int a1, a2;
+        if (lim >= 32) chunk_min2<false>(v, negScale, 32, a1, a2); else chunk_min2<true>(v, negScale, lim, a1, a2);
+        a1 += colBase;                                   // a chunk always has its first column: a1 is a real key
+        if (a2 != 0x7fffffff) a2 += colBase;
+        second = min(max(best, a1), min(second, a2));
+        best = min(best, a1);
+    }
+}
+
+// This thread's row of one accumulator stage, kEpiCols columns from taddr: tcgen05.ld of chunk k+1 is in flight while
+// chunk k is reduced.
+template <bool kTwo>
+__device__ __forceinline__ void epi_tile(uint32_t taddr, int valid, int col0, int negScale, int& best, int& second) {
+    int va[32], vb[32];
+    tmem_ld32(taddr, va);
+#pragma unroll
+    for (int k = 0; k < kEpiCols / 32; k += 2) {
+        tmem_ld_wait(va);
+        tmem_ld32(taddr + (k + 1) * 32, vb);
+        epi_chunk<kTwo>(va, valid - k * 32, col0 + k * 32, negScale, best, second);
+        tmem_ld_wait(vb);
+        if (k + 2 < kEpiCols / 32) tmem_ld32(taddr + (k + 2) * 32, va);
+        epi_chunk<kTwo>(vb, valid - (k + 1) * 32, col0 + (k + 1) * 32, negScale, best, second);
+    }
+}
+
 struct Item { int pair, dir, mt, nX, nY, slotX, slotY; bool rows, work; };
 
 __device__ __forceinline__ Item decode_item(int item, int mTiles, const int* featCount, int slotA0, int maxkp) {
@@ -197,6 +231,7 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
     const uint32_t fullA = sBar, emptyA = sBar + 16, fullB = sBar + 32, emptyB = sBar + 48, accFull = sBar + 64, accEmpty = sBar + 80;
     const uint32_t sTmem = sBar + 96;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int sPart[2 * kTileM];            // partial (best, runner-up) of the upper column half
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -224,52 +259,44 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
 
     if (warp < kEpiWarps) {
         // ---------------------------------------------------------------- epilogue
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (the hardware's lane quarter of a warp) and columns
+        // [kEpiCols (w / 4), +kEpiCols) of every tile; the two partial minima of a row meet in shared memory per item
         uint32_t accUse = 0;
-        const uint32_t laneBase = ((uint32_t)(warp * 32)) << 16;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int rowInTile = quarter * 32 + lane;
+        const uint32_t laneBase = ((uint32_t)(quarter * 32)) << 16;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const Item it = decode_item(item, mTiles, ob.featCount, slotA0, pg.maxkp);
             if (!it.rows) continue;
-            const int row = it.mt * kTileM + threadIdx.x;
+            const int row = it.mt * kTileM + rowInTile;
             int best = 0x7fffffff, second = 0x7fffffff;
             const bool two = kSecond && it.dir == 0;
-            auto consume = [&](const int (&v)[32], int lim, int colBase) {
-                if (lim <= 0) return;
-                if (two) {
-                    int a1, a2;
-                    if (lim >= 32) chunk_min2<false>(v, negScale, 32, a1, a2); else chunk_min2<true>(v, negScale, lim, a1, a2);
-                    a1 += colBase;                                   // a chunk always has its first column: a1 is a real key
-                    if (a2 != 0x7fffffff) a2 += colBase;
-                    second = min(max(best, a1), min(second, a2));
-                    best = min(best, a1);
-                } else {
-                    best = min(best, (lim >= 32 ? chunk_min<false>(v, negScale, 32) : chunk_min<true>(v, negScale, lim)) + colBase);
-                }
-            };
             if (it.work) {
                 const int nTiles = (it.nY + kTileN - 1) / kTileN;
                 for (int nt = 0; nt < nTiles; ++nt, ++accUse) {
                     const uint32_t cs = accUse & 1;
                     mbar_wait(accFull + 8 * cs, (accUse >> 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t taddr = tmemBase + laneBase + cs * kTileN;
-                    const int col0 = nt * kTileN;
-                    const int valid = it.nY - col0;          // > 0
-                    int va[32], vb[32];
-                    tmem_ld32(taddr, va);
-#pragma unroll
-                    for (int k = 0; k < kTileN / 32; k += 2) {
-                        tmem_ld_wait(va);
-                        tmem_ld32(taddr + (k + 1) * 32, vb);
-                        consume(va, valid - k * 32, col0 + k * 32);
-                        tmem_ld_wait(vb);
-                        if (k + 2 < kTileN / 32) tmem_ld32(taddr + (k + 2) * 32, va);
-                        consume(vb, valid - (k + 1) * 32, col0 + (k + 1) * 32);
-                    }
+                    const uint32_t taddr = tmemBase + laneBase + cs * kTileN + half * kEpiCols;
+                    const int col0 = nt * kTileN + half * kEpiCols;
+                    const int valid = it.nY - col0;          // may be <= 0 for the upper half of the last tile
+                    if (kSecond && two) epi_tile<true>(taddr, valid, col0, negScale, best, second);
+                    else epi_tile<false>(taddr, valid, col0, negScale, best, second);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(accEmpty + 8 * cs);
                 }
             }
-            if (row < it.nX) {
+            if (kEpiWarps > 4) {
+                if (half == 1) { sPart[rowInTile] = best; sPart[kTileM + rowInTile] = second; }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                if (half == 0) {
+                    const int b1 = sPart[rowInTile], b2 = sPart[kTileM + rowInTile];
+                    second = min(max(best, b1), min(second, b2));
+                    best = min(best, b1);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");      // sPart is free for the next item
+            }
+            if (half == 0 && row < it.nX) {
                 const size_t o = ((size_t)(pair0 + it.pair) * 2 + it.dir) * pg.maxkp + row;
                 if (two) {            // k_match_sort's ratio path: plain index, distance, runner-up distance
                     pb.nnIdx[o] = best == 0x7fffffff ? -1 : (best & 0xFFFF);
