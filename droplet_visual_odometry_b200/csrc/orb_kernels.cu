@@ -456,27 +456,41 @@ struct KeyHarris {  // harris float bits in the high word
     __device__ __forceinline__ static float key(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 };
 
-__device__ __forceinline__ int harris_sums_warp(const uint8_t* img, int pitch, int x, int y, int lane, int& b_out, int& c_out) {
-    // 7x7 block of Sobel-3 products: lanes 0..48 (two rounds) each take one block pixel
-    int a = 0, bb = 0, c = 0;
-    for (int i = lane; i < 49; i += 32) {
-        int dy = i / 7 - 3, dx = i % 7 - 3;
-        const uint8_t* p = img + (size_t)(y + dy) * pitch + (x + dx);
-        int p00 = p[-pitch - 1], p01 = p[-pitch], p02 = p[-pitch + 1];
-        int p10 = p[-1], p12 = p[1];
-        int p20 = p[pitch - 1], p21 = p[pitch], p22 = p[pitch + 1];
-        int ix = (p12 - p10) * 2 + (p02 - p00) + (p22 - p20);
-        int iy = (p21 - p01) * 2 + (p20 - p00) + (p22 - p02);
-        a += ix * ix;
-        bb += iy * iy;
-        c += ix * iy;
+// 7x7 block of Sobel-3 products for kN keypoints at once: lanes 0..48 (two rounds) each take one block pixel of every
+// keypoint, and the 18 * kN byte loads are all issued before the first use (one memory latency for the group -- the
+// one-keypoint-at-a-time form left each warp waiting on L2/DRAM ~27 times per level).
+template <int kN>
+__device__ __forceinline__ void harris_sums_warp(const uint8_t* img, int pitch, const int (&xs)[kN], const int (&ys)[kN], int lane,
+                                                 int (&a_out)[kN], int (&b_out)[kN], int (&c_out)[kN]) {
+    int px[kN][2][8];
+#pragma unroll
+    for (int q = 0; q < kN; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = lane + 32 * r;
+            const bool on = i < 49;
+            const int dy = i / 7 - 3, dx = i % 7 - 3;
+            const uint8_t* p = img + (size_t)(ys[q] + dy) * pitch + (xs[q] + dx);
+            px[q][r][0] = on ? p[-pitch - 1] : 0; px[q][r][1] = on ? p[-pitch] : 0; px[q][r][2] = on ? p[-pitch + 1] : 0;
+            px[q][r][3] = on ? p[-1] : 0; px[q][r][4] = on ? p[1] : 0;
+            px[q][r][5] = on ? p[pitch - 1] : 0; px[q][r][6] = on ? p[pitch] : 0; px[q][r][7] = on ? p[pitch + 1] : 0;
+        }
+#pragma unroll
+    for (int q = 0; q < kN; ++q) {
+        int a = 0, bb = 0, c = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int* v = px[q][r];
+            const int ix = (v[4] - v[3]) * 2 + (v[2] - v[0]) + (v[7] - v[5]);
+            const int iy = (v[6] - v[1]) * 2 + (v[5] - v[0]) + (v[7] - v[2]);
+            a += ix * ix;
+            bb += iy * iy;
+            c += ix * iy;
+        }
+        a_out[q] = __reduce_add_sync(0xffffffffu, a);
+        b_out[q] = __reduce_add_sync(0xffffffffu, bb);
+        c_out[q] = __reduce_add_sync(0xffffffffu, c);
     }
-    a = __reduce_add_sync(0xffffffffu, a);
-    bb = __reduce_add_sync(0xffffffffu, bb);
-    c = __reduce_add_sync(0xffffffffu, c);
-    b_out = bb;
-    c_out = c;
-    return a;
 }
 
 // Single-thread accessor (median-of-3 step).
@@ -631,14 +645,31 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
 
     // ---- Harris response of the survivors (un-blurred level)
     const uint8_t* img = b.pyr + (size_t)slot * g.slotStride + lv.off;
-    for (int i = warp; i < n1; i += blockDim.x >> 5) {
-        uint32_t c = work1[i];
-        int x = c & 0xFFF, y = (c >> 12) & 0xFFF;
-        int sb, sc_;
-        int sa = harris_sums_warp(img, lv.pitch, x, y, lane, sb, sc_);
-        if (lane == 0) {
-            float r = harris_from_sums(sa, sb, sc_);
-            pairs[i] = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(c & 0xFFFFFFu);
+    {
+        constexpr int kH = 2;                      // keypoints per warp per round (3 spills at 64 registers)
+        const int nW = blockDim.x >> 5;
+        for (int i0 = warp; i0 < n1; i0 += nW * kH) {
+            uint32_t cc[kH];
+            int xs[kH], ys[kH], sa[kH], sb[kH], sc_[kH];
+#pragma unroll
+            for (int q = 0; q < kH; ++q) {
+                const int i = min(i0 + q * nW, n1 - 1);      // past the end: recompute the last one, result unused
+                cc[q] = work1[i];
+                xs[q] = cc[q] & 0xFFF; ys[q] = (cc[q] >> 12) & 0xFFF;
+            }
+            harris_sums_warp<kH>(img, lv.pitch, xs, ys, lane, sa, sb, sc_);
+            if (lane < kH) {
+                int a = sa[0], bq = sb[0], cq = sc_[0];
+                uint32_t c = cc[0];
+#pragma unroll
+                for (int q = 1; q < kH; ++q)
+                    if (lane == q) { a = sa[q]; bq = sb[q]; cq = sc_[q]; c = cc[q]; }
+                const int i = i0 + lane * nW;
+                if (i < n1) {
+                    const float r = harris_from_sums(a, bq, cq);
+                    pairs[i] = ((unsigned long long)__float_as_uint(r) << 32) | (unsigned long long)(c & 0xFFFFFFu);
+                }
+            }
         }
     }
     __syncthreads();   // pairs[] written with plain stores by this block, read back below after the barrier
