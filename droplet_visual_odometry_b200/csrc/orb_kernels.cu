@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     __shared__ __align__(16) uint16_t list1[(kTileH + 2) * (kTileW + 2)];
     constexpr int kList2Cap = (kTileH + 2) * (kTileW + 2);
     __shared__ uint16_t list2[kList2Cap];
-    __shared__ int s_n1, s_n2, s_warpTot[8];
+    __shared__ int s_n1, s_n2;
     __shared__ int s_rowcnt[kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
@@ -212,19 +212,17 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
             passw[sw] = pass;
             cnt += __popc(pass);
         }
-        // one CTA-wide exclusive scan of the per-thread survivor counts, then every thread appends its own survivors
+        // warp-wide exclusive scan of the per-thread survivor counts; each warp reserves its share of list1 with one
+        // shared atomic (the list order is irrelevant: every later phase writes through maps), then every thread appends
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int n = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += n;
         }
-        if (lane == 31) s_warpTot[tid >> 5] = incl;
-        __syncthreads();
         int base = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) base += (w < (tid >> 5)) ? s_warpTot[w] : 0;
-        if (tid == 255) s_n1 = base + incl;
+        if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
         int pos = base + incl - cnt;
 #pragma unroll
         for (int sw = 0; sw < kSweeps; ++sw) {
