@@ -107,20 +107,25 @@ DVO_HD int imax3(int a, int b, int c) {
 // Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
 // Returns the passing polarities: bit 0 = a 9-arc with every d > t, bit 1 = a 9-arc with every d < -t (0 = not a corner).
 DVO_HD int fast_corner_polarity16(int v, const int* p, int t) {
+    const int lo = v - t, hi = v + t;
+#if defined(__CUDA_ARCH__)
+    // Both comparisons of a ring pixel in one IMAD: W = p * 0xFFFF + C has p + 0x7FFF - hi in its high half (bit 31 <=> p > hi)
+    // and 0x8000 + lo - 1 - p in its low half (bit 15 <=> p < lo); neither half leaves [0, 0xFFFF], so they do not interact.
+    // acc = (acc >> 1) | (W & 0x80008000) collects the sixteen flag pairs: high half = "p > hi" ring mask, low half = "p < lo".
+    const uint32_t C = ((uint32_t)(0x7FFF - hi) << 16) + (uint32_t)(0x8000 + lo - 1);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = (acc >> 1) | (((uint32_t)p[k] * 0xFFFFu + C) & 0x80008000u);
+    const uint32_t brighter = acc & 0xFFFFu, darker = acc >> 16;
+#else
     // bit per ring pixel, shifted in at the bottom (ring order reversed -- contiguity is what matters):
     // sign(p - lo) <=> p < v - t <=> d > t ;  sign(hi - p) <=> p > v + t <=> d < -t
     uint32_t brighter = 0, darker = 0;
-    const int lo = v - t, hi = v + t;
-#pragma unroll
     for (int k = 0; k < 16; ++k) {
-#if defined(__CUDA_ARCH__)
-        brighter = __funnelshift_l((uint32_t)(p[k] - lo), brighter, 1);
-        darker = __funnelshift_l((uint32_t)(hi - p[k]), darker, 1);
-#else
         brighter = (brighter << 1) | ((uint32_t)(p[k] - lo) >> 31);
         darker = (darker << 1) | ((uint32_t)(hi - p[k]) >> 31);
-#endif
     }
+#endif
     return (ring_has9(brighter) ? 1 : 0) | (ring_has9(darker) ? 2 : 0);
 }
 DVO_HD bool fast_is_corner16(int v, const int* p, int t) { return fast_corner_polarity16(v, p, t) != 0; }
