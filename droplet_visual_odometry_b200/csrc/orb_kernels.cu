@@ -228,11 +228,10 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         for (int sw = 0; sw < kSweeps; ++sw) {
             uint32_t m = passw[sw];
             const int code0 = (sw * kRowsPerSweep + qrow + 3) * kFastBoxW + 12 + 4 * qx;
-            while (m) {
-                const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
-                list1[pos++] = (uint16_t)(code0 + (bit >> 3));
-                m &= m - 1;
-            }
+            // four predicated appends instead of a divergent walk over the set bits (the longest lane set the pace)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (m & (0x80u << (8 * q))) list1[pos++] = (uint16_t)(code0 + q);
         }
     }
     __syncthreads();
