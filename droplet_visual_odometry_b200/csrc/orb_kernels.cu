@@ -17,6 +17,18 @@
 
 namespace dvo {
 
+// Shared-memory atomics as single instructions: the callers already aggregate per warp (or hit distinct addresses), so
+// the warp-aggregation sequence the compiler wraps around atomicAdd() is pure overhead here.
+__device__ __forceinline__ int smem_atom_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void smem_red_add(int* p, int v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+
 static long long g_launches = 0;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -221,17 +233,26 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
             if (lane >= o) incl += n;
         }
         int base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(&s_n1, incl);
+        if (lane == 31 && incl > 0) base = smem_atom_add(&s_n1, incl);
         base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + incl - cnt;
+        // four predicated appends per sweep through a 32-bit shared address (no divergent walk over the set bits, and no
+        // re-derivation of the list base under every predicate)
+        uint32_t la = (uint32_t)__cvta_generic_to_shared(list1) + 2u * (uint32_t)(base + incl - cnt);
 #pragma unroll
         for (int sw = 0; sw < kSweeps; ++sw) {
-            uint32_t m = passw[sw];
+            const uint32_t m = passw[sw];
             const int code0 = (sw * kRowsPerSweep + qrow + 3) * kFastBoxW + 12 + 4 * qx;
-            // four predicated appends instead of a divergent walk over the set bits (the longest lane set the pace)
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (m & (0x80u << (8 * q))) list1[pos++] = (uint16_t)(code0 + q);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                    "and.b32 t, %2, %3;\n\t"
+                    "setp.ne.u32 p, t, 0;\n\t"
+                    "@p st.shared.u16 [%0], %1;\n\t"
+                    "@p add.u32 %0, %0, 2;\n\t}"
+                    : "+r"(la)
+                    : "h"((uint16_t)(code0 + q)), "r"(m), "r"(0x80u << (8 * q))
+                    : "memory");
         }
     }
     __syncthreads();
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         const bool corner = pol != 0;
         const unsigned m = __ballot_sync(0xffffffffu, corner);
         int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_n2, __popc(m));
+        if (lane == 0 && m) base = smem_atom_add(&s_n2, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
     }
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         const bool keep = sv > nmax;
         if (keep) {
             outmap[(cy - 1) * kTileW + (cx - 1)] = (uint8_t)sv;
-            atomicAdd(&s_rowcnt[cy - 1], 1);
+            smem_red_add(&s_rowcnt[cy - 1], 1);
         }
     }
     __syncthreads();
