@@ -16,6 +16,13 @@
 #include <cstdlib>
 
 namespace dvo {
+
+// Shared-memory counter update as one RED instruction: the callers have already reduced over the warp, so the
+// warp-aggregation sequence the compiler wraps around atomicAdd() is overhead.
+__device__ __forceinline__ void smem_red_add(int* p, int v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
 void debug_sync(const char* name, cudaStream_t st);
 
 // ransacState layout (ints)
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(kRansacThreads, 2) k_ransac(PairGeom pg, PairB
                     int good = (v0 && sampson_inlier(E, p0.x, p0.y, p0.z, p0.w, t32, tlo, thi)) ? 1 : 0;
                     good += (v1 && sampson_inlier(E, p1.x, p1.y, p1.z, p1.w, t32, tlo, thi)) ? 1 : 0;
                     good = __reduce_add_sync(0xffffffffu, good);
-                    if (lane == 0 && good) atomicAdd(&acc[h][k], good);
+                    if (lane == 0 && good) smem_red_add(&acc[h][k], good);
                 }
             }
         }
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(kRansacThreads) k_ex_score(PairGeom pg, PairBu
                 int good = (v0 && sampson_inlier(E, p0.x, p0.y, p0.z, p0.w, t32, tlo, thi)) ? 1 : 0;
                 good += (v1 && sampson_inlier(E, p1.x, p1.y, p1.z, p1.w, t32, tlo, thi)) ? 1 : 0;
                 good = __reduce_add_sync(0xffffffffu, good);
-                if (lane == 0 && good) atomicAdd(&s_good[h][k], good);
+                if (lane == 0 && good) smem_red_add(&s_good[h][k], good);
             }
         }
     }
