@@ -13,6 +13,8 @@ $CMD > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_' -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_l_$tag.log 2>&1
 if [ -z "$2" ]; then
 $CMD > gpurun_out/plain2_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'^k_' -s 110 -c 24 -f -o gpurun_out/prof_$tag $CMD > gpurun_out/ncu_f_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'^k_' -s 120 -c 26 -f -o gpurun_out/prof_$tag $CMD > gpurun_out/ncu_f_$tag.log 2>&1
 fi
+python tools/time_configs.py > gpurun_out/other_configs_$tag.json 2>> gpurun_out/bench_$tag.err; echo "configs rc=$?"
+for ing in grey bgr; do python bench.py --steps 10 --warmup 3 --ingest $ing > gpurun_out/bench_ingest_${ing}_$tag.json 2>> gpurun_out/bench_$tag.err; echo "ingest $ing rc=$?"; done
 cat gpurun_out/bench_$tag.json
