@@ -227,6 +227,24 @@ def level_pixel_counts(ctx):
     return [ctx.level_size(L)[0] * ctx.level_size(L)[1] for L in range(ctx.nlevels)]
 
 
+def _bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this process (and therefore the pinned host buffers it allocates, first touch) on the CPU
+    socket the GPU hangs off, so that eight ranks' H2D streams do not all cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (max(os.sched_getaffinity(0)) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -240,6 +258,8 @@ def run_b200(a):
         raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None     # pinned host frames land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -398,7 +418,8 @@ def run_b200(a):
 
     # ---- CPU baseline beside it (rank 0, bounded sample of the same workload)
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:      # the CPU leg is an N=1 measurement
+        os.sched_setaffinity(0, all_cpus)
         workers = os.cpu_count() or 1
         pps = min(max(8, 2 * workers), 128)
         fr = (frames[:pps + 1, :, :, 0] if a.ingest == "bgr" else frames[:pps + 1]).contiguous().cpu().numpy()
@@ -419,7 +440,7 @@ def run_b200(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
                "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
                "data": "synthetic",
-               "config": {"workload": workload_name(a), "pairs_per_step": B, "frames_resident_MB": round(frames.numel() / 1e6, 1),
+               "config": {"workload": workload_name(a), "pairs_per_step": B, "numa_bound_cpus": numa, "frames_resident_MB": round(frames.numel() / 1e6, 1),
                           "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
                               B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
                           "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",

@@ -533,3 +533,23 @@ def test_tensor_core_ratio_matcher_equals_popc_ratio_matcher(env, na, nb):
     assert got[0][0] == got[1][0] and np.array_equal(got[0][1], got[1][1])
     if nb >= 2 and na > 100:
         assert got[0][0] > 0
+
+
+def test_tensor_core_matcher_large_keypoint_sets(env):
+    """6000-feature context, ragged counts over many row blocks and column tiles: tensor-core engine equals the POPC engine."""
+    rng = np.random.default_rng(77)
+    na, nb = 5321, 4999
+    da = rng.integers(0, 256, size=(na, 32), dtype=np.uint8)
+    db = da[rng.permutation(na)[:nb]].copy()
+    db[rng.random(nb) < 0.5, 7] ^= 0x10                       # half of them one bit away, the rest exact copies
+    pa = rng.uniform(40, 1200, size=(na, 2)).astype(np.float32)
+    pb = rng.uniform(40, 1000, size=(nb, 2)).astype(np.float32)
+    got = []
+    for engine in (0, 1):
+        ctx = env.native.Context(1280, 1024, nfeatures=6000, max_frames=2, nn_engine=engine)
+        ctx.set_features(0, pa, da); ctx.set_features(1, pb, db)
+        ctx.pairs(0, 0, 1, env.K)
+        p = ctx.poses(0, 1)[0]
+        got.append((int(p["n_matches"]), ctx.pair_arrays(0, p["n_matches"])["matches"]))
+        ctx.close()
+    assert got[0][0] == got[1][0] == nb and np.array_equal(got[0][1], got[1][1])
