@@ -727,15 +727,21 @@ __global__ void __launch_bounds__(256) k_angle_pack(OrbGeom g, OrbBuffers b, int
     const int slot = slot0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.x * 8 + warp;
-    int total = 0, L = -1, idx = 0;
+    // level of keypoint gi: lane i holds level i's survivor count, a three-step scan gives the running totals and one
+    // ballot counts the levels that end at or before gi (was an 8-iteration scalar loop in every lane: 20 % of the kernel)
     const int* finCount = b.finCount + slot * kMaxLevels;
-    for (int i = 0; i < g.nlevels; ++i) {
-        int c = finCount[i];
-        if (L < 0 && gi < total + c) { L = i; idx = gi - total; }
-        total += c;
+    int incl = lane < g.nlevels ? finCount[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kMaxLevels; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
     }
+    const int total = __shfl_sync(0xffffffffu, incl, g.nlevels - 1);
+    const int L = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels && gi >= incl));
+    const int before = __shfl_sync(0xffffffffu, incl, max(L - 1, 0));
+    const int idx = gi - (L > 0 ? before : 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) b.featCount[slot] = min(total, g.maxkp);
-    if (L < 0 || gi >= g.maxkp) return;
+    if (gi >= total || gi >= g.maxkp) return;
     const LevelGeom lv = g.lv[L];
     const uint32_t xy = b.finXY[(size_t)slot * g.finPerSlot + lv.finBase + idx];
     const float resp = b.finResp[(size_t)slot * g.finPerSlot + lv.finBase + idx];
