@@ -944,24 +944,31 @@ __global__ void __launch_bounds__(256) k_brief(OrbGeom g, OrbBuffers b, int slot
     const uint8_t* pb8 = reinterpret_cast<const uint8_t*>(patch) + kBriefR * (4 * kBriefWords) + (cx - xa);
     const uint8_t* center = img + (size_t)cy * lv.pitch + cx;
     unsigned byte = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t pq = __ldg(&d_brief_pattern_t[j * 32 + lane]);
+    // two separate loops (the test is warp-uniform): with both sources in one loop body the compiler computed the global
+    // fallback addresses for every sample and predicated the loads -- a sixth of the kernel's instructions
+    auto rotate = [&](uint32_t pq, int& ix0, int& iy0, int& ix1, int& iy1) {
         const float x0f = (float)(signed char)(pq & 0xFF), y0f = (float)(signed char)((pq >> 8) & 0xFF);
         const float x1f = (float)(signed char)((pq >> 16) & 0xFF), y1f = (float)(signed char)(pq >> 24);
-        int ix0 = __float2int_rn(fsub(fmul(x0f, ca), fmul(y0f, sa)));
-        int iy0 = __float2int_rn(fadd(fmul(x0f, sa), fmul(y0f, ca)));
-        int ix1 = __float2int_rn(fsub(fmul(x1f, ca), fmul(y1f, sa)));
-        int iy1 = __float2int_rn(fadd(fmul(x1f, sa), fmul(y1f, ca)));
-        int t0, t1;
-        if (inside) {
-            t0 = pb8[iy0 * (4 * kBriefWords) + ix0];
-            t1 = pb8[iy1 * (4 * kBriefWords) + ix1];
-        } else {                               // never for cv2-selected keypoints (31-px border); keeps odd inputs safe
-            t0 = center[iy0 * lv.pitch + ix0];
-            t1 = center[iy1 * lv.pitch + ix1];
+        ix0 = __float2int_rn(fsub(fmul(x0f, ca), fmul(y0f, sa)));
+        iy0 = __float2int_rn(fadd(fmul(x0f, sa), fmul(y0f, ca)));
+        ix1 = __float2int_rn(fsub(fmul(x1f, ca), fmul(y1f, sa)));
+        iy1 = __float2int_rn(fadd(fmul(x1f, sa), fmul(y1f, ca)));
+    };
+    if (inside) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int ix0, iy0, ix1, iy1;
+            rotate(__ldg(&d_brief_pattern_t[j * 32 + lane]), ix0, iy0, ix1, iy1);
+            const int t0 = pb8[iy0 * (4 * kBriefWords) + ix0], t1 = pb8[iy1 * (4 * kBriefWords) + ix1];
+            byte |= (unsigned)(t0 < t1) << j;
         }
-        byte |= (unsigned)(t0 < t1) << j;
+    } else {                                   // never for cv2-selected keypoints (31-px border); keeps odd inputs safe
+        for (int j = 0; j < 8; ++j) {
+            int ix0, iy0, ix1, iy1;
+            rotate(__ldg(&d_brief_pattern_t[j * 32 + lane]), ix0, iy0, ix1, iy1);
+            const int t0 = center[iy0 * lv.pitch + ix0], t1 = center[iy1 * lv.pitch + ix1];
+            byte |= (unsigned)(t0 < t1) << j;
+        }
     }
     b.featDesc[o * 32 + lane] = (uint8_t)byte;
 }
