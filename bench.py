@@ -181,9 +181,38 @@ def run_reference(a):
 
 # ================================================================================================ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (every 2 ms -- the timed region of
+    a default run is under 100 ms, too short for nvidia-smi's start-up), nvidia-smi -lms as the fallback."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
+        self.p, self.f, self.thread = None, None, None
+        self.sm, self.mx, self.reasons = [], [], set()
+        try:
+            import pynvml, threading
+            pynvml.nvmlInit()
+            self.h = None
+            try:                                           # CUDA_VISIBLE_DEVICES may renumber: look the device up by UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except Exception:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self._poll()                                   # fail here, not in the thread, if a query is unsupported
+            self.halt = threading.Event()
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
@@ -191,8 +220,32 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _poll(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        for name, bit in self.BITS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self.halt.is_set():
+            try:
+                self._poll()
+            except Exception:
+                break
+            self.halt.wait(0.002)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            sm = self.sm[1:] or self.sm                    # the first sample predates the timed region
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(self.mx)), reasons=sorted(self.reasons), samples=len(sm),
+                       source="nvml")
+            return out
         if self.p is None:
             return out
         time.sleep(0.15)
@@ -218,7 +271,7 @@ class ClockSampler:
         self.f.close()
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
