@@ -6,18 +6,24 @@
 // so the whole 2000 x 2000 distance matrix of a frame pair is one int8 GEMM with K = 256 and exact int32 accumulators,
 // and the XOR+POPC kernel's bound (POPC runs on the 16-lane XU pipe: 0.79 ms per 148 pairs at best) disappears.
 //
-//   k_expand_desc   bits -> +-1 bytes, one row of 256 B per descriptor
-//   k_nn_tensor     persistent, one CTA per SM, warp-specialised:
-//       warps 0-3   epilogue: thread t owns accumulator row t (TMEM lane t): tcgen05.ld 32 columns at a time, one IMAD per
+//   k_expand_desc   bits -> +-1 bytes, 256 B per descriptor, written in the order the MMA reads its operands
+//   k_nn_tensor     persistent, one CTA per SM, warp-specialised (320 threads):
+//       warps 0-7   epilogue.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (a warp can only reach its own lane quarter), i.e.
+//                   thread t of the quarter owns accumulator row t, and columns [128 (w / 4), +128) of every tile:
+//                   tcgen05.ld 32 columns at a time (the next load in flight while one chunk is reduced), one IMAD per
 //                   element builds the packed key (distance << 16 | column) and VIMNMX3 keeps the row minimum; ties go to
-//                   the lowest column, as cv2's batchDistance does.  No cross-thread reduction and no atomics: the reverse
+//                   the lowest column, as cv2's batchDistance does.  The two partial minima of a row meet in shared
+//                   memory once per work item.  No cross-thread reduction inside a tile and no atomics: the reverse
 //                   direction (train -> query) is simply the transposed product, scheduled as its own work items.
-//       warp 4      one lane issues tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, eight per tile) into a double-buffered
+//                   kSecond (ratio matcher): forward rows also keep the runner-up key (knnMatch k = 2).
+//       warp 8      one lane issues tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, eight per tile) into a double-buffered
 //                   TMEM accumulator (2 x 256 columns) and commits to the mbarriers that free the operand stages
-//       warp 5      producer: one lane streams the operand tiles with cp.async.bulk (mbarrier complete_tx).  k_expand_desc
+//       warp 9      producer: one lane streams the operand tiles with cp.async.bulk (mbarrier complete_tx).  k_expand_desc
 //                   already stores the rows in the canonical no-swizzle K-major core-matrix order (8 rows x 16 B
 //                   contiguous; K-adjacent core matrices 128 B apart, 8-row groups 2 KB apart): a tile is one block
 //   A work item is (pair, direction, 128-row block); it streams every 256-column tile of the other frame past its rows.
+//   Measured (148 pairs of 2000 x 2000): 0.21 ms + 0.03 ms expansion = 2.55 int8 POP/s; bound by L2 -> SM operand traffic
+//   (2.6 GB per batch).  Every mbarrier wait is a bounded spin that traps, so a protocol error fails the launch loudly.
 #include "dvo_internal.cuh"
 
 namespace dvo {
