@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--ref-pairs-per-step", type=int, default=0, help="reference arm: pairs per step (0 = 2 x workers, min 8)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--matcher-engine", default="tensor", choices=["tensor", "popc"],
+                    help="cross-check matcher: int8 tcgen05 GEMM (default) or the XOR+POPC integer-pipe kernel (BASELINE north_star item 4 as written)")
     ap.add_argument("--ingest", default="none", choices=["none", "grey", "bgr"],
                     help="widened path (SURVEY 8f row 2): frames arrive distorted (grey or BGR) and cv.cvtColor + cv.undistort "
                          "run inside the timed region on both arms; default: the BASELINE workload (undistorted mono frames)")
@@ -319,7 +321,8 @@ def run_b200(a):
     B, K_steps, W_steps = a.batch, max(a.steps, 1), max(a.warmup, 3)      # timing rule: at least 3 untimed warm-up steps
     n_frames = (K_steps + W_steps) * B + 1
     frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * 5000)
-    ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local)
+    ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local,
+                          nn_engine=0 if a.matcher_engine == "tensor" else 1)
     Kpose = Kmat
     if a.ingest != "none":
         Kpose = ingest_new_K(Kmat)
@@ -437,7 +440,7 @@ def run_b200(a):
                 bytes_total = alg_bytes_per_frame[name] * B * groups
                 st["achieved_GBps"] = round(bytes_total / (tms * 1e-3) / 1e9, 2)
                 st["frac_of_hbm_peak"] = round(st["achieved_GBps"] / peak, 4)
-            if name == "k_nn":
+            if name == "k_nn" and a.matcher_engine == "tensor":
                 # cross-check matcher = int8 GEMM on the tensor cores (k_expand_desc + k_nn_tensor): both directions of the
                 # N x N x 256 distance matrix, 2 ops per multiply-add; peak = 2 x the measured bf16 rate (int8 runs at twice
                 # bf16 on sm_100a), else 2 x 2250 nominal
@@ -446,6 +449,11 @@ def run_b200(a):
                 int8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
                 st["frac_of_int8_tensor_peak"] = round(st["int8_tops"] / int8_peak, 4)
                 st["int8_peak_tops"] = int8_peak
+            if name == "k_nn" and a.matcher_engine == "popc":
+                # every distance is computed once (row and column minima from the same popcounts): N*N*8 POPC32 per pair,
+                # against the nominal XU-pipe rate of 16 POPC/clk/SM (the kernel executes 6 per distance: two carry-save adders)
+                st["gpopc_per_s"] = round(nkp * nkp * 8 * B * cnt / (tms * 1e-3) / 1e9, 1)
+                st["frac_of_popc_peak"] = round(st["gpopc_per_s"] * 1e9 / (148 * 16 * 1.965e9), 4)
             stages[name] = st
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         dms, dcnt = prof[dom]
@@ -493,7 +501,7 @@ def run_b200(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
                "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
                "data": "synthetic",
-               "config": {"workload": workload_name(a), "pairs_per_step": B, "numa_bound_cpus": numa, "frames_resident_MB": round(frames.numel() / 1e6, 1),
+               "config": {"workload": workload_name(a), "pairs_per_step": B, "matcher_engine": a.matcher_engine, "numa_bound_cpus": numa, "frames_resident_MB": round(frames.numel() / 1e6, 1),
                           "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
                               B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
                           "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
