@@ -214,6 +214,18 @@ static int build_tensor_maps(dvo_ctx* ctx, const OrbBuffers& ob, TensorMaps& tma
             ctx->err = buf;
             return DVO_E_CUDA;
         }
+        for (int v = 0; v < 2 && L + 1 < ctx->og.nlevels; ++v) {      // level L as the source of k_pyr_down(L + 1)
+            cuuint32_t sbox[3] = {(cuuint32_t)kPyrSrcW, (cuuint32_t)(v == 0 ? kPyrSrcH : kPyrSrcHSmall), 1};
+            r = encode(&tmaps.pyrSrc[v][L], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ob.pyr + lv.off, dims, strides, sbox, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                char buf[128];
+                snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed for pyramid source level %d: CUresult %d", L, (int)r);
+                ctx->err = buf;
+                return DVO_E_CUDA;
+            }
+        }
     }
     return 0;
 }

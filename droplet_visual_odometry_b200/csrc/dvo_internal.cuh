@@ -80,8 +80,10 @@ struct OrbBuffers {
 };
 
 struct TensorMaps {
-    CUtensorMap pyr[kMaxLevels];
+    CUtensorMap pyr[kMaxLevels];          // FAST tile boxes (kFastBoxW x kFastBoxH), one map per level
+    CUtensorMap pyrSrc[2][kMaxLevels];    // k_pyr_down source windows of level L: [0] kPyrSrcW x kPyrSrcH, [1] kPyrSrcW x kPyrSrcHSmall
 };
+constexpr int kPyrSrcW = 176, kPyrSrcH = 82, kPyrSrcHSmall = 24;   // source window of a 128 x 64 / 128 x 16 output tile at ratio 1.2
 
 struct PairGeom {
     int maxkp;            // descriptor capacity per slot

@@ -33,6 +33,7 @@ static long long g_launches = 0;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
     int L = 0;
 #pragma unroll
@@ -48,9 +49,13 @@ __device__ __forceinline__ int find_level_by_tile(const OrbGeom& g, int tile) {
 // gathering bytes from global memory with 64-bit addresses.  Each thread owns 4 adjacent output columns (x coefficients in
 // registers) and walks `rows` output rows (8 on the large levels, 2 on the small ones so that the grid fills the machine).
 // Clamping at the right / bottom edge is implicit: the coefficient tables give weight 0 to the tap past the last pixel.
-constexpr int kPyrSrcW = 176, kPyrSrcH = 82;
-__global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L, int slot0, int rows) {
-    __shared__ __align__(16) uint8_t tile[kPyrSrcH * kPyrSrcW];
+// kUseTma: the window is one cp.async.bulk.tensor.3d box (176 x 82, or 176 x 24 on the two-row launches) of the source level's
+// tensor map, landed through an mbarrier; out-of-range rows / columns arrive as zeros and only ever meet a zero weight.
+template <bool kUseTma>
+__global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, const __grid_constant__ CUtensorMap srcMap, int L, int slot0,
+                                                  int rows) {
+    __shared__ __align__(128) uint8_t tile[kPyrSrcH * kPyrSrcW];
+    __shared__ __align__(8) unsigned long long bar;
     const LevelGeom& d = g.lv[L];
     const LevelGeom& s = g.lv[L - 1];
     const int slot = slot0 + blockIdx.z;
@@ -63,16 +68,44 @@ __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L
     const int sx0 = (int)(__ldg(tx + x0) >> 16);
     const int sy0 = (int)(__ldg(ty + y0) >> 16), sy1 = (int)(__ldg(ty + yLast) >> 16) + 1;
     const int ax0 = sx0 & ~15;
-    // always the full 176-byte rows (compile-time divisor below); what lies beyond sx1 is never used, and reading it is
-    // safe: rows are pitch-padded and the buffers end with slack
-    constexpr int nVec = kPyrSrcW / 16;
-    const int nRow = min(sy1 - sy0 + 1, kPyrSrcH);
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < nRow * nVec; i += 256) {
-        const int r = i / nVec, v = i - r * nVec;
-        // row s.h (one past the image) is allocated padding; it only ever meets a zero weight
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)min(sy0 + r, s.h) * s.pitch + ax0) + v);
-        *reinterpret_cast<uint4*>(tile + r * kPyrSrcW + v * 16) = q;
+    if (kUseTma) {
+        const uint32_t barAddr = smem_u32(&bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr),
+                         "r"(kPyrSrcW * (rows >= 8 ? kPyrSrcH : kPyrSrcHSmall))
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                    smem_u32(tile)),
+                "l"(reinterpret_cast<uint64_t>(&srcMap)), "r"(barAddr), "r"(ax0), "r"(sy0), "r"(slot)
+                : "memory");
+        }
+        __syncthreads();                       // the barrier is initialised before anyone polls it
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; ++spin) {      // bounded: a lost copy traps instead of hanging the GPU
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0)
+                : "memory");
+            if (spin > (1u << 24)) __trap();
+        }
+    } else {
+        // always the full 176-byte rows (compile-time divisor below); what lies beyond sx1 is never used, and reading it is
+        // safe: rows are pitch-padded and the buffers end with slack
+        constexpr int nVec = kPyrSrcW / 16;
+        const int nRow = min(sy1 - sy0 + 1, kPyrSrcH);
+        for (int i = tid; i < nRow * nVec; i += 256) {
+            const int r = i / nVec, v = i - r * nVec;
+            // row s.h (one past the image) is allocated padding; it only ever meets a zero weight
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)min(sy0 + r, s.h) * s.pitch + ax0) + v);
+            *reinterpret_cast<uint4*>(tile + r * kPyrSrcW + v * 16) = q;
+        }
     }
     __syncthreads();
     const int x4 = x0 + threadIdx.x * 4;
@@ -116,7 +149,6 @@ __global__ void __launch_bounds__(256) k_pyr_down(OrbGeom g, OrbBuffers b, int L
 }
 
 // =========================================================================================== A.2 FAST + NMS
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool kUseTma>
 __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, const __grid_constant__ TensorMaps tm, int slot0) {
@@ -1156,7 +1188,8 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
         const int rows = ctas8 >= 148 * 16 ? 8 : 2;
         dim3 grid((g.lv[L].w + 127) / 128, (g.lv[L].h + 8 * rows - 1) / (8 * rows), nSlots);
         ProfScope ps_(PF_PYR, st);
-        k_pyr_down<<<grid, dim3(32, 8), 0, st>>>(g, b, L, slot0, rows);
+        if (useTma) k_pyr_down<true><<<grid, dim3(32, 8), 0, st>>>(g, b, tmaps->pyrSrc[rows >= 8 ? 0 : 1][L - 1], L, slot0, rows);
+        else k_pyr_down<false><<<grid, dim3(32, 8), 0, st>>>(g, b, tmaps->pyr[0], L, slot0, rows);
         ++g_launches;
         debug_sync("k_pyr_down", st);
     }
