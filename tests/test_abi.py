@@ -67,3 +67,34 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "import cv2" not in text.replace("import cv2 as cv", "") or \
                     f == "visual_odometry_v3.py", f
+
+
+def test_shipped_kernels_carry_the_blackwell_instructions():
+    """The built library is sm_100a code and the kernels DESIGN.md describes as TMA-staged / tensor-core really are:
+    cuobjdump -sass must show UTMALDG (TMA tile load) in k_fast_nms<1> and k_pyr_down<1>, and UTCIMMA (tcgen05.mma int8),
+    LDTM (tcgen05.ld) and UBLKCP (bulk copy) in k_nn_tensor.  Static check, no GPU needed."""
+    import shutil, subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "droplet_visual_odometry_b200", "libdvo.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    body, cur = {}, None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            body[cur] = []
+        elif cur:
+            body[cur].append(line)
+
+    def ops(substr):
+        names = [k for k in body if substr in k]
+        assert names, substr
+        return "\n".join("\n".join(body[k]) for k in names)
+    assert "UTMALDG" in ops("k_fast_nmsILb1")
+    assert "UTMALDG" in ops("k_pyr_downILb1")
+    nn = ops("k_nn_tensorILb0")
+    for op in ("UTCIMMA", "LDTM", "UTCBAR", "UBLKCP", "SYNCS"):
+        assert op in nn, op
+    assert "POPC" in ops("4k_nnILb1")                   # the integer-pipe matcher engine is shipped too
