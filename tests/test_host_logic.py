@@ -147,3 +147,21 @@ def test_frame_folder_reads_in_name_order_and_by_slice(tmp_path):
         cv2.imwrite(str(d2 / ("frame_%03d.png" % i)), imgs[i])
     fp = S.FrameFolder(str(d2))
     assert fp.timestamps == [0.0, 1.0, 2.0] and np.array_equal(fp[0:3], imgs[:3])
+
+
+def test_bench_host_helpers_degrade_without_a_gpu():
+    """bench.py's measurement helpers are best effort: without NVML / nvidia-smi they return empty results, never raise,
+    and never change the process's CPU affinity."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    bound = bench._bind_to_gpu_numa_node(0)
+    assert bound is None or (isinstance(bound, int) and bound > 0)
+    if bound is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+    clocks = bench.ClockSampler(0).stop()
+    assert set(clocks) >= {"sm_mhz", "sm_max_mhz", "reasons"}
