@@ -104,6 +104,11 @@ DVO_HD int imax3(int a, int b, int c) {
 #endif
 }
 
+// Both threshold comparisons of one ring pixel p (0..255) in one multiply-add: bit 31 <=> p > hi, bit 15 <=> p < lo, for
+// lo = v - t, hi = v + t with v, t in 0..255 (checked exhaustively on the host: tests/hostsim hs_fast_ring_flags_check).
+DVO_HD uint32_t fast_ring_flag_bias(int lo, int hi) { return ((uint32_t)(0x7FFF - hi) << 16) + (uint32_t)(0x8000 + lo - 1); }
+DVO_HD uint32_t fast_ring_flags(uint32_t p, uint32_t bias) { return (p * 0xFFFFu + bias) & 0x80008000u; }
+
 // Corner test of one pixel: true iff 9 contiguous ring pixels are all darker than v - t or all brighter than v + t.
 // Returns the passing polarities: bit 0 = a 9-arc with every d > t, bit 1 = a 9-arc with every d < -t (0 = not a corner).
 DVO_HD int fast_corner_polarity16(int v, const int* p, int t) {
@@ -112,10 +117,10 @@ DVO_HD int fast_corner_polarity16(int v, const int* p, int t) {
     // Both comparisons of a ring pixel in one IMAD: W = p * 0xFFFF + C has p + 0x7FFF - hi in its high half (bit 31 <=> p > hi)
     // and 0x8000 + lo - 1 - p in its low half (bit 15 <=> p < lo); neither half leaves [0, 0xFFFF], so they do not interact.
     // acc = (acc >> 1) | (W & 0x80008000) collects the sixteen flag pairs: high half = "p > hi" ring mask, low half = "p < lo".
-    const uint32_t C = ((uint32_t)(0x7FFF - hi) << 16) + (uint32_t)(0x8000 + lo - 1);
+    const uint32_t C = fast_ring_flag_bias(lo, hi);
     uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc = (acc >> 1) | (((uint32_t)p[k] * 0xFFFFu + C) & 0x80008000u);
+    for (int k = 0; k < 16; ++k) acc = (acc >> 1) | fast_ring_flags((uint32_t)p[k], C);
     const uint32_t brighter = acc & 0xFFFFu, darker = acc >> 16;
 #else
     // bit per ring pixel, shifted in at the bottom (ring order reversed -- contiguity is what matters):

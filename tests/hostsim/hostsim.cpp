@@ -124,6 +124,22 @@ int hs_fast_prefilter_check(const uint8_t* img, int w, int h, int pitch, int t, 
     return missed;
 }
 
+// exhaustive check of the one-IMAD ring comparison used by the device build of fast_corner_polarity16: returns the number of
+// (v, t, p) triples, all in 0..255, where a flag differs from the plain comparison (must be 0)
+int hs_fast_ring_flags_check() {
+    int bad = 0;
+    for (int v = 0; v < 256; ++v)
+        for (int t = 0; t < 256; ++t) {
+            const int lo = v - t, hi = v + t;
+            const uint32_t bias = fast_ring_flag_bias(lo, hi);
+            for (int p = 0; p < 256; ++p) {
+                const uint32_t f = fast_ring_flags((uint32_t)p, bias);
+                if (((f >> 31) & 1u) != (uint32_t)(p > hi) || ((f >> 15) & 1u) != (uint32_t)(p < lo) || (f & ~0x80008000u)) ++bad;
+            }
+        }
+    return bad;
+}
+
 float hs_harris(int a, int b, int c) { return harris_from_sums(a, b, c); }
 float hs_fast_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 int hs_five_point(const double* x1, const double* x2, double* models) { return five_point_solve(x1, x2, models); }

@@ -191,3 +191,9 @@ def test_cheirality_pair_equals_two_separate_triangulations(hostsim, golden):
         sep = hostsim.hs_cheirality(ptr(Rg), ptr(tg), *args) | (hostsim.hs_cheirality(ptr(Rg), ptr(tn), *args) << 1)
         bad += int(both != sep)
     assert bad == 0
+
+
+def test_fast_one_imad_ring_comparison_is_exact_for_every_pixel_centre_and_threshold(hostsim):
+    """The device build of the exact FAST test folds `p > v + t` and `p < v - t` into one multiply-add per ring pixel;
+    all 2^24 (v, t, p) combinations agree with the plain comparisons."""
+    assert hostsim.hs_fast_ring_flags_check() == 0
