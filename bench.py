@@ -469,7 +469,7 @@ def run_b200(a):
             achieved = alg * dcnt / (dms * 1e-3) / 1e9
         # DRAM traffic per frame of the streaming kernels from the committed `ncu --set full` capture (profiles/, 1280x1024,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch / frames per launch); null for other sizes / kernels
-        ncu_traffic_per_frame = {"k_fast_nms": (213.71e6 + 176.72e6) / 50, "k_blur": (217.39e6 + 172.41e6) / 50} \
+        ncu_traffic_per_frame = {"k_fast_nms": (218e6 + 181e6) / 50, "k_blur": (222e6 + 178e6) / 50} \
             if (a.width, a.height) == (1280, 1024) else {}
         traffic = int(ncu_traffic_per_frame[dom] * B) if dom in ncu_traffic_per_frame else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
