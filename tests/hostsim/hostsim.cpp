@@ -140,6 +140,22 @@ int hs_fast_ring_flags_check() {
     return bad;
 }
 
+// exhaustive check of the shift-and-AND 9-arc detector against a direct cyclic run-length count: number of 16-bit ring
+// masks on which they disagree (must be 0)
+int hs_ring_has9_check() {
+    int bad = 0;
+    for (uint32_t m = 0; m < 65536u; ++m) {
+        int best = 0;
+        for (int s = 0; s < 16; ++s) {
+            int run = 0;
+            while (run < 16 && ((m >> ((s + run) & 15)) & 1u)) ++run;
+            if (run > best) best = run;
+        }
+        if (ring_has9(m) != (best >= 9)) ++bad;
+    }
+    return bad;
+}
+
 float hs_harris(int a, int b, int c) { return harris_from_sums(a, b, c); }
 float hs_fast_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 int hs_five_point(const double* x1, const double* x2, double* models) { return five_point_solve(x1, x2, models); }

@@ -197,3 +197,7 @@ def test_fast_one_imad_ring_comparison_is_exact_for_every_pixel_centre_and_thres
     """The device build of the exact FAST test folds `p > v + t` and `p < v - t` into one multiply-add per ring pixel;
     all 2^24 (v, t, p) combinations agree with the plain comparisons."""
     assert hostsim.hs_fast_ring_flags_check() == 0
+
+
+def test_ring_has9_equals_cyclic_run_length_on_all_65536_masks(hostsim):
+    assert hostsim.hs_ring_has9_check() == 0
