@@ -10,7 +10,9 @@ a folder of frames instead of a rosbag, the same stamped_traj_estimate_{absolute
 ``distortion_coeffs`` (default) or ``camera_matrix`` / ``distortion_coefficients`` (``--controlled``).  ``--undistort``
 feeds distorted frames through the GPU ingest (cv.undistort with getOptimalNewCameraMatrix(alpha=1), as
 ros_img_msg_to_opencv_image does, :115-135); without it frames are taken as already undistorted, like the images the
-reference hands to visual_odometry_calculations.
+reference hands to visual_odometry_calculations.  Like the reference (:297-306), findEssentialMat / recoverPose get the
+ORIGINAL camera matrix even after undistorting to the new one; ``--pose-with-new-camera-matrix`` uses the new matrix
+instead (geometrically consistent, but not what the reference computes).
 """
 import argparse
 import os
@@ -45,6 +47,8 @@ def main(argv=None):
     ap.add_argument("--controlled", action="store_true")
     ap.add_argument("--undistort", action="store_true")
     ap.add_argument("--color", action="store_true", help="decode frames as BGR (grey conversion then happens on the GPU)")
+    ap.add_argument("--pose-with-new-camera-matrix", action="store_true",
+                    help="with --undistort: pass getOptimalNewCameraMatrix's result to the pose stage (the reference passes the original K)")
     a = ap.parse_args(argv)
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -61,7 +65,9 @@ def main(argv=None):
         import cv2 as cv      # one-off host call, as the reference makes it (:117-123); the per-frame remap runs on the GPU
         h, w = frames[0].shape[:2]
         new_K, _ = cv.getOptimalNewCameraMatrix(K, D, (w, h), 1, (w, h))
-        undistort, Kpose = (K, D, new_K), new_K
+        undistort = (K, D, new_K)
+        if a.pose_with_new_camera_matrix:
+            Kpose = new_K
     elif a.color:
         raise SystemExit("--color needs --undistort (the GPU ingest does the grey conversion)")
     rec, paths = S.extract_trajectory(frames, Kpose, a.out_dir, nfeatures=a.nfeatures, batch=a.batch, device=local,

@@ -17,10 +17,35 @@ _LIB_PATH = os.path.join(_HERE, "libdvo.so")
 DVO_MATCH_CROSSCHECK = 0
 DVO_MATCH_KNN_RATIO = 1
 PAIR_OK, PAIR_TOO_FEW_MATCHES, PAIR_NO_MODEL = 0, 1, 2
+FRAME_TIES_TRUNCATED, FRAME_CANDIDATES_TRUNCATED, FRAME_KEYPOINTS_TRUNCATED = 1, 2, 4
+DVO_E_CAPACITY = -3
 
 
 class DvoError(RuntimeError):
     pass
+
+
+def describe_frame_flags(f):
+    names = [(FRAME_TIES_TRUNCATED, "ties at the Harris boundary truncated"), (FRAME_CANDIDATES_TRUNCATED, "FAST candidate list truncated"),
+             (FRAME_KEYPOINTS_TRUNCATED, "keypoint capacity exceeded")]
+    return ", ".join(n for b, n in names if f & b) or "none"
+
+
+def triangulate_points(P0, P1, pts0, pts1):
+    """cv.triangulatePoints(P0, P1, pts0.T, pts1.T) -> (4, n), computed by libdvo's host restatement of OpenCV's DLT + Jacobi
+    SVD: unnormalised homogeneous points with cv2's sign (visual_odometry_v3.py:265).  float64 in, float64 out."""
+    lib = load_library()
+    P0 = np.ascontiguousarray(np.asarray(P0, dtype=np.float64).reshape(3, 4))
+    P1 = np.ascontiguousarray(np.asarray(P1, dtype=np.float64).reshape(3, 4))
+    a = np.ascontiguousarray(np.asarray(pts0, dtype=np.float64).reshape(-1, 2))
+    b = np.ascontiguousarray(np.asarray(pts1, dtype=np.float64).reshape(-1, 2))
+    if len(a) != len(b):
+        raise ValueError("triangulate_points: the two point sets differ in length")
+    X = np.zeros((4, len(a)), dtype=np.float64)
+    rc = lib.dvo_triangulate_points_host(P0.ctypes.data, P1.ctypes.data, a.ctypes.data, b.ctypes.data, len(a), X.ctypes.data)
+    if rc != 0:
+        raise DvoError("dvo_triangulate_points_host failed (%d)" % rc)
+    return X
 
 
 class dvo_config(ctypes.Structure):
@@ -44,7 +69,7 @@ class dvo_pair_arrays(ctypes.Structure):
 
 POSE_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("E", "<f8", (9,)), ("status", "<i4"), ("n_matches", "<i4"),
                        ("n_inliers", "<i4"), ("n_good", "<i4"), ("ransac_iters", "<i4"), ("best_iter", "<i4"),
-                       ("candidate", "<i4"), ("n_prev", "<i4"), ("n_cur", "<i4"), ("reserved", "<i4")])
+                       ("candidate", "<i4"), ("n_prev", "<i4"), ("n_cur", "<i4"), ("frame_flags", "<i4")])
 assert POSE_DTYPE.itemsize == 208
 
 _lib = None
@@ -76,6 +101,11 @@ def load_library():
     lib.dvo_orb.argtypes = [vp, ci, ci, vp]
     lib.dvo_get_features.argtypes = [vp, ci, ctypes.POINTER(dvo_features), vp]
     lib.dvo_pairs.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_match.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_pose_pairs.argtypes = [vp, ci, ci, ci, vp, vp]
+    lib.dvo_get_match_count.argtypes = [vp, ci, ctypes.POINTER(ci), vp]
+    lib.dvo_get_frame_flags.argtypes = [vp, ci, ci, vp, vp]
+    lib.dvo_triangulate_points_host.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.dvo_set_features.argtypes = [vp, ci, vp, vp, ci, ci, vp]
     lib.dvo_pose_points.argtypes = [vp, ci, vp, vp, ci, vp, ci, vp]
     lib.dvo_get_poses.argtypes = [vp, ci, ci, vp, ci, vp]
@@ -216,6 +246,21 @@ class Context:
     def orb(self, slot0, n):
         self._check(self.lib.dvo_orb(self._h, slot0, n, self._stream()), "dvo_orb")
 
+    def frame_flags(self, slot0=0, n=1):
+        """FRAME_* bits of slots [slot0, slot0+n) (synchronises); non-zero = the slot's keypoint set was truncated."""
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.dvo_get_frame_flags(self._h, slot0, n, out.ctypes.data, self._stream()), "dvo_get_frame_flags")
+        return out
+
+    def check_frames(self, slot0=0, n=1):
+        """Raise (never return a truncated feature set silently) when a slot could not hold everything cv2 keeps."""
+        f = self.frame_flags(slot0, n)
+        if f.any():
+            bad = int(np.flatnonzero(f)[0])
+            raise DvoError("DVO_E_CAPACITY (%d): frame slot %d holds a truncated keypoint set (flags 0x%x: %s) -- cv2 keeps every "
+                           "tie at the retainBest boundary and this image has more of them than quota + 64 per level"
+                           % (DVO_E_CAPACITY, slot0 + bad, int(f[bad]), describe_frame_flags(int(f[bad]))))
+
     def features(self, slot):
         """Host copies of one slot's detectAndCompute output (synchronises)."""
         t, M = self.torch, self.max_keypoints
@@ -230,12 +275,28 @@ class Context:
                          count.data_ptr(), M)
         self._check(self.lib.dvo_get_features(self._h, slot, ctypes.byref(f), self._stream()), "dvo_get_features")
         n = int(count.item())
+        self.check_frames(slot, 1)
         return {"pt": pt[:n].cpu().numpy(), "size": size[:n].cpu().numpy(), "angle": angle[:n].cpu().numpy(),
                 "response": resp[:n].cpu().numpy(), "octave": octave[:n].cpu().numpy(), "desc": desc[:n].cpu().numpy()}
 
     def pairs(self, slot0, pair0, n, K):
         Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
         self._check(self.lib.dvo_pairs(self._h, slot0, pair0, n, Kc.ctypes.data, self._stream()), "dvo_pairs")
+
+    def match(self, slot0, pair0, n, K):
+        """bf.match + sorted + KeyPoint_convert only (dvo_match); read the result with match_count + pair_arrays."""
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        self._check(self.lib.dvo_match(self._h, slot0, pair0, n, Kc.ctypes.data, self._stream()), "dvo_match")
+
+    def pose(self, slot0, pair0, n, K):
+        """findEssentialMat + recoverPose on the correspondences dvo_match left in the pair slots (dvo_pose_pairs)."""
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        self._check(self.lib.dvo_pose_pairs(self._h, slot0, pair0, n, Kc.ctypes.data, self._stream()), "dvo_pose_pairs")
+
+    def match_count(self, pair=0):
+        c = ctypes.c_int()
+        self._check(self.lib.dvo_get_match_count(self._h, pair, ctypes.byref(c), self._stream()), "dvo_get_match_count")
+        return c.value
 
     def set_features(self, slot, pt, desc):
         """Overwrite a slot with caller keypoint coordinates (n,2) f32 and descriptors (n,32) u8 (host arrays)."""

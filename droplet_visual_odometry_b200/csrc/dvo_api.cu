@@ -5,13 +5,14 @@
 #include <cstring>
 #include <algorithm>
 #include "dvo_internal.cuh"
+#include "mathcore.cuh"
 
 namespace dvo {
 long long orb_launch_count();
 long long pair_launch_count();
-void orb_kernels_init();
-void pair_kernels_init(int sortBytes);
-void pair_kernels_init_exhaustive(int rngCount);
+cudaError_t orb_kernels_init();
+cudaError_t pair_kernels_init(int sortBytes);
+cudaError_t pair_kernels_init_exhaustive(int rngCount);
 void prof_enable(bool on);
 bool prof_enabled();
 void prof_collect(double* ms, int* count, int n);
@@ -107,6 +108,7 @@ static int alloc_orb_buffers(dvo_ctx* ctx, OrbBuffers& b) {
     DA(b.featCS, S * g.maxkp * 2);
     DA(b.featDesc, S * g.maxkp * 32);
     DA(b.featCount, S);
+    DA(b.frameFlags, S);
 #undef DA
     return 0;
 }
@@ -332,7 +334,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
     pb.descXRows = nn_tensor_rows(g.maxkp);
     if (pg.nnTensor) {
         DA(pb.descX, (P + 1) * (size_t)pb.descXRows * 256);
-        nn_tensor_init();
+        CK(nn_tensor_init());
     }
     DA(pb.matches, P * M * 3);
     DA(pb.matchCount, P);
@@ -354,7 +356,7 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
         CK(cudaMemcpy(d_st, st.data(), st.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
         pb.rngStates = d_st;
         DA(pb.exStart, P * (size_t)pg.maxIters);
-        pair_kernels_init_exhaustive(pg.rngCount);
+        CK(pair_kernels_init_exhaustive(pg.rngCount));
         DA(pb.exModels, P * (size_t)pg.maxIters * kMaxModels * 9);
         DA(pb.exCount, P * (size_t)pg.maxIters);
         DA(pb.exGood, P * (size_t)pg.maxIters * kMaxModels);
@@ -399,8 +401,8 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
             CK(cudaEventCreateWithFlags(&ctx->evCarryCopied[i], cudaEventDisableTiming));
         }
     }
-    orb_kernels_init();
-    pair_kernels_init((int)(pg.sortCap * sizeof(uint32_t)));
+    CK(orb_kernels_init());
+    CK(pair_kernels_init((int)(pg.sortCap * sizeof(uint32_t))));
     CK(cudaDeviceSynchronize());
     ctx->launchBase = orb_launch_count() + pair_launch_count();
     return DVO_OK;
@@ -616,6 +618,14 @@ int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stre
     return DVO_OK;
 }
 
+int dvo_get_frame_flags(dvo_ctx* ctx, int slot0, int n, int32_t* h_flags, void* stream) {
+    if (!ctx || !h_flags || n < 0 || slot0 < 0 || slot0 + n > ctx->nSlots) return DVO_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) CK(cudaMemcpyAsync(h_flags, ctx->ob.frameFlags + slot0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DVO_OK;
+}
+
 int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which, uint8_t* d_dst, void* stream) {
     if (!ctx || !d_dst || slot < 0 || slot >= ctx->nSlots || level < 0 || level >= ctx->og.nlevels || which < 0 || which > 2)
         return DVO_E_INVALID;
@@ -654,6 +664,38 @@ int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* 
     return DVO_OK;
 }
 
+int dvo_match(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream) {
+    if (!ctx || !K || n < 0 || slot0 < 0 || slot0 + n + (n > 0 ? 1 : 0) > ctx->nSlots || pair0 < 0 || pair0 + n > ctx->nPairs) {
+        if (ctx) ctx->err = "dvo_match: slot/pair range out of bounds";
+        return DVO_E_INVALID;
+    }
+    if (ctx->pg.sortCap * sizeof(uint32_t) > 200 * 1024) {
+        ctx->err = "dvo_match: nfeatures too large for the in-shared-memory match sort (max ~49000 keypoints)";
+        return DVO_E_CAPACITY;
+    }
+    launch_match(ctx->og, ctx->ob, ctx->pg, ctx->pb, slot0, pair0, n, K, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+int dvo_pose_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream) {
+    if (!ctx || !K || n < 0 || pair0 < 0 || pair0 + n > ctx->nPairs || (slot0 >= 0 && slot0 + n + (n > 0 ? 1 : 0) > ctx->nSlots)) {
+        if (ctx) ctx->err = "dvo_pose_pairs: slot/pair range out of bounds";
+        return DVO_E_INVALID;
+    }
+    launch_ransac_pose(ctx->og, ctx->ob, ctx->pg, ctx->pb, slot0 < 0 ? -1 : slot0, pair0, n, K, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return DVO_OK;
+}
+
+int dvo_get_match_count(dvo_ctx* ctx, int pair, int* h_count, void* stream) {
+    if (!ctx || !h_count || pair < 0 || pair >= ctx->nPairs) return DVO_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h_count, ctx->pb.matchCount + pair, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DVO_OK;
+}
+
 int dvo_set_features(dvo_ctx* ctx, int slot, const float* pt, const uint8_t* desc, int n, int kind, void* stream) {
     if (!ctx || slot < 0 || slot >= ctx->nSlots || n < 0 || (n > 0 && (!pt || !desc))) return DVO_E_INVALID;
     if (n > ctx->og.maxkp) { ctx->err = "dvo_set_features: n exceeds dvo_max_keypoints"; return DVO_E_CAPACITY; }
@@ -665,6 +707,7 @@ int dvo_set_features(dvo_ctx* ctx, int slot, const float* pt, const uint8_t* des
         CK(cudaMemcpyAsync(ctx->ob.featDesc + o * 32, desc, 32 * (size_t)n, k, st));
     }
     CK(cudaMemcpyAsync(ctx->ob.featCount + slot, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->ob.frameFlags + slot, 0, sizeof(int), st));
     CK(cudaStreamSynchronize(st));   // &n is a stack variable
     return DVO_OK;
 }
@@ -728,7 +771,7 @@ __global__ void k_copy_features(OrbGeom g, OrbBuffers a, OrbBuffers b, int src, 
             b.featOctave[d0 + i] = a.featOctave[so + i];
             b.featXY[d0 + i] = a.featXY[so + i];
         }
-        if (i == 0) b.featCount[dst] = a.featCount[src];
+        if (i == 0) { b.featCount[dst] = a.featCount[src]; b.frameFlags[dst] = a.frameFlags[src]; }
     }
 }
 
@@ -878,6 +921,19 @@ int dvo_sequence(dvo_ctx* ctx, const uint8_t* frames, int n_frames, size_t pitch
     if (kind == 1) {
         CK(cudaStreamSynchronize((cudaStream_t)stream));
         memcpy(poses, dst, (size_t)(n_frames - 1) * sizeof(dvo_pose));
+    }
+    return DVO_OK;
+}
+
+// Host-side: cv.triangulatePoints of get_scaling_factor_from_triangulation (visual_odometry_v3.py:265) for a handful of
+// fiducial corners.  Same arithmetic as OpenCV (4x4 DLT, cv::SVD's Jacobi path), so the unnormalised vectors -- sign
+// included -- are the ones the reference measures its marker distance on.
+int dvo_triangulate_points_host(const double* P0, const double* P1, const double* pts0, const double* pts1, int n, double* X) {
+    if (!P0 || !P1 || n < 0 || (n > 0 && (!pts0 || !pts1 || !X))) return DVO_E_INVALID;
+    for (int i = 0; i < n; ++i) {
+        double q[4];
+        dvo::cv_triangulate_point(P0, P1, pts0[2 * i], pts0[2 * i + 1], pts1[2 * i], pts1[2 * i + 1], q);
+        for (int k = 0; k < 4; ++k) X[(size_t)k * n + i] = q[k];
     }
     return DVO_OK;
 }

@@ -74,6 +74,7 @@ struct OrbBuffers {
     float* featCS;           // [slots][maxkp][2] cos, sin of the keypoint angle (float32 roundings of the float64 values)
     uint8_t* featDesc;       // [slots][maxkp][32]
     int* featCount;          // [slots]
+    int* frameFlags;         // [slots] DVO_FRAME_* bits of the last dvo_orb on the slot (0 = the feature set is complete)
     const uint32_t* resizeTab;   // per level: x table then y table, packed ofs<<16 | c1
     const uint32_t* tileInfo;    // [tilesPerFrame] level | tileX << 4 | tileY << 16 for the 128x32 image-kernel tiles
     int resizeTabOff[kMaxLevels][2];
@@ -171,9 +172,11 @@ void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& i
 void launch_load_frames(const OrbGeom& g, const OrbBuffers& b, const uint8_t* d_src, int n, size_t pitch, size_t frameStride,
                         int slot0, cudaStream_t st);
 int nn_tensor_rows(int maxkp);
-void nn_tensor_init();
+cudaError_t nn_tensor_init();
 void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
                       int nPairs, int numSms, cudaStream_t st);
+void launch_match(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
+                  int pair0, int nPairs, const double* K, cudaStream_t st);
 void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0,
                   int pair0, int nPairs, const double* K, cudaStream_t st);
 

@@ -321,6 +321,93 @@ DVO_HDN void jacobi_onesided(double* A, double* V) {
     }
 }
 
+// cv::SVD::compute(A, w, u, vt) for an NxN double matrix the way OpenCV runs it for small matrices (JacobiSVDImpl_ on the
+// transposed copy; matrices with fewer than 25 rows never reach LAPACK): one-sided Jacobi on the columns of A with cv2's
+// rotation formula, stop rule (|p| <= 10 eps sqrt(ab)) and sweep limit, then a selection sort by descending singular value.
+// No sign normalisation happens anywhere, so the rows of Vt -- in particular the null vector in the last row -- carry the
+// sign this exact sequence of rotations leaves them with; cv.triangulatePoints returns that row unscaled.
+template <int N>
+DVO_HDN void cv_jacobi_svd(const double* A /*NxN row-major*/, double* W, double* Vt /*NxN, rows = right singular vectors*/) {
+    double At[N * N];
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < N; ++k) At[i * N + k] = A[k * N + i];
+    const double eps = DBL_EPSILON * 10;
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < N; ++k) sd += At[i * N + k] * At[i * N + k];
+        W[i] = sd;
+        for (int k = 0; k < N; ++k) Vt[i * N + k] = (i == k) ? 1.0 : 0.0;
+    }
+    const int max_iter = N > 30 ? N : 30;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                double* Ai = At + i * N;
+                double* Aj = At + j * N;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < N; ++k) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < N; ++k) {
+                    const double t0 = c * Ai[k] + s * Aj[k];
+                    const double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+                double* Vi = Vt + i * N;
+                double* Vj = Vt + j * N;
+                for (int k = 0; k < N; ++k) {
+                    const double t0 = c * Vi[k] + s * Vj[k];
+                    const double t1 = -s * Vi[k] + c * Vj[k];
+                    Vi[k] = t0; Vj[k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < N; ++k) sd += At[i * N + k] * At[i * N + k];
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < N - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < N; ++k)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double tw = W[i]; W[i] = W[j]; W[j] = tw;
+            for (int k = 0; k < N; ++k) { double tv = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = tv; }
+        }
+    }
+}
+
+// cv.triangulatePoints(P0, P1, x0, x1) for one correspondence: rows (x P[2] - P[0], y P[2] - P[1]) of both views, the last row
+// of cv::SVD's Vt, unnormalised and with cv2's sign (visual_odometry_v3.py:265 measures distances on these raw vectors).
+DVO_HDN void cv_triangulate_point(const double* P0 /*3x4*/, const double* P1, double x0, double y0, double x1, double y1, double* X) {
+    double A[16], W[4], Vt[16];
+    for (int k = 0; k < 4; ++k) {
+        A[k] = x0 * P0[8 + k] - P0[k];
+        A[4 + k] = y0 * P0[8 + k] - P0[4 + k];
+        A[8 + k] = x1 * P1[8 + k] - P1[k];
+        A[12 + k] = y1 * P1[8 + k] - P1[4 + k];
+    }
+    cv_jacobi_svd<4>(A, W, Vt);
+    for (int k = 0; k < 4; ++k) X[k] = Vt[12 + k];
+}
+
 // cv2.decomposeEssentialMat: R1 = U W Vt, R2 = U Wt Vt, t = U[:,2] with det(U) = det(Vt) = +1.
 DVO_HDN void decompose_essential(const double* E, double* R1, double* R2, double* t) {
     double A[9], V[9];

@@ -377,9 +377,10 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
 
 int nn_tensor_rows(int maxkp) { return ((maxkp + kTileN - 1) / kTileN) * kTileN; }
 
-void nn_tensor_init() {
-    cudaFuncSetAttribute(k_nn_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    cudaFuncSetAttribute(k_nn_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+cudaError_t nn_tensor_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_nn_tensor<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_nn_tensor<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 }
 
 void launch_nn_tensor(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,

@@ -680,7 +680,8 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
     unsigned long long* pairs = b.pairs + (size_t)slot * g.candPerSlot + lv.candBase;
     uint32_t* listL = b.selList + ((size_t)slot * g.candPerSlot + lv.candBase) * 2;
     uint32_t* listR = listL + lv.candCap;
-    const int n = min(b.candCount[slot * kMaxLevels + L], lv.candCap);
+    const int nRaw = b.candCount[slot * kMaxLevels + L];
+    const int n = min(nRaw, lv.candCap);
 
     // ---- pass 1: retainBest(2 * quota) on the FAST score, order-exact
     const bool inSmem1 = (size_t)n * sizeof(uint32_t) <= (size_t)smemBytes;
@@ -736,8 +737,11 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers
         BlockAcc<unsigned long long, KeyHarris> acc{work2, n1, listL, listR, &sh};
         n2 = retain_best_paired(acc, n1, lv.quota, kSelectSeqTail);
     }
-    int flags = 0;
-    if (n2 > lv.finCap) { n2 = lv.finCap; flags |= 1; }
+    // cv2 keeps EVERY tie at the Harris boundary (retainBest); room for quota + kFinSlack of them exists per level.  More
+    // than that (periodic or saturated images) cannot be represented: the frame is flagged and every reader of its
+    // features fails loudly (dvo_get_frame_flags, dvo_pose.frame_flags) instead of returning a truncated keypoint set.
+    int flags = nRaw > lv.candCap ? DVO_FRAME_CANDIDATES_TRUNCATED : 0;
+    if (n2 > lv.finCap) { n2 = lv.finCap; flags |= DVO_FRAME_TIES_TRUNCATED; }
     uint32_t* finXY = b.finXY + (size_t)slot * g.finPerSlot + lv.finBase;
     float* finResp = b.finResp + (size_t)slot * g.finPerSlot + lv.finBase;
     for (int i = tid; i < n2; i += blockDim.x) {
@@ -772,7 +776,12 @@ __global__ void __launch_bounds__(256) k_angle_pack(OrbGeom g, OrbBuffers b, int
     const int L = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels && gi >= incl));
     const int before = __shfl_sync(0xffffffffu, incl, max(L - 1, 0));
     const int idx = gi - (L > 0 ? before : 0);
-    if (blockIdx.x == 0 && threadIdx.x == 0) b.featCount[slot] = min(total, g.maxkp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b.featCount[slot] = min(total, g.maxkp);
+        int f = total > g.maxkp ? DVO_FRAME_KEYPOINTS_TRUNCATED : 0;
+        for (int l = 0; l < g.nlevels; ++l) f |= b.selDbg[(slot * kMaxLevels + l) * 4 + 3];
+        b.frameFlags[slot] = f;
+    }
     if (gi >= total || gi >= g.maxkp) return;
     const LevelGeom lv = g.lv[L];
     const uint32_t xy = b.finXY[(size_t)slot * g.finPerSlot + lv.finBase + idx];
@@ -1252,8 +1261,9 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     debug_sync("k_brief", st);
 }
 
-void orb_kernels_init() {
-    cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectSmemBytes);
+cudaError_t orb_kernels_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectSmemBytes);
+    if (e != cudaSuccess) return e;
     uint32_t t[8 * 32];
     for (int lane = 0; lane < 32; ++lane)
         for (int j = 0; j < 8; ++j) {
@@ -1261,7 +1271,7 @@ void orb_kernels_init() {
             t[j * 32 + lane] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
                                ((uint32_t)(uint8_t)p[3] << 24);
         }
-    cudaMemcpyToSymbol(d_brief_pattern_t, t, sizeof t);
+    return cudaMemcpyToSymbol(d_brief_pattern_t, t, sizeof t);
 }
 
 }  // namespace dvo

@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(256) k_pose_final(OrbGeom og, OrbBuffers ob, P
         out.n_cur = slotA0 >= 0 ? ob.featCount[slotA0 + pi + 1] : M;
         out.ransac_iters = rs[RS_NITERS];
         out.best_iter = rs[RS_BESTITER];
-        out.reserved = rs[RS_BESTMODEL];
+        out.frame_flags = slotA0 >= 0 ? (ob.frameFlags[slotA0 + pi] | ob.frameFlags[slotA0 + pi + 1]) : 0;
         if (!rs[RS_HASBEST]) {
             out.status = (M < 5) ? DVO_PAIR_TOO_FEW_MATCHES : DVO_PAIR_NO_MODEL;
             for (int j = 0; j < 9; ++j) { out.R[j] = (j % 4 == 0) ? 1.0 : 0.0; out.E[j] = 0.0; }
@@ -711,14 +711,15 @@ __global__ void __launch_bounds__(256) k_pose_final(OrbGeom og, OrbBuffers ob, P
 static long long g_pair_launches = 0;
 long long pair_launch_count() { return g_pair_launches; }
 
-void pair_kernels_init_exhaustive(int rngCount) {
-    cudaFuncSetAttribute(k_ex_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, rngCount);
+cudaError_t pair_kernels_init_exhaustive(int rngCount) {
+    return cudaFuncSetAttribute(k_ex_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, rngCount);
 }
 
-void pair_kernels_init(int sortBytes) {
+cudaError_t pair_kernels_init(int sortBytes) {
     // contexts too large for the in-smem sort (points-only use) never launch k_match_sort: dvo_pairs refuses them
     if (sortBytes > 48 * 1024 && sortBytes <= 200 * 1024)
-        cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortBytes);
+        return cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sortBytes);
+    return cudaSuccess;
 }
 
 // Points-only entry: normalise caller correspondences and reset the RANSAC state (no matching stage).
@@ -758,7 +759,7 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
         ProfScope ps_(PF_RANSAC, st);
         const int chunks = (pg.maxIters + kRansacGroups - 1) / kRansacGroups;
         int slices = 1;      // enough CTAs to fill the machine a few times over, at least ~2048 correspondences per slice
-        while (slices < 64 && (long long)chunks * nPairs * slices < 148 * 8 && pg.maxkp / (slices * 2) >= 2048) slices *= 2;
+        while (slices < 64 && (long long)chunks * nPairs * slices < (long long)pg.numSms * 8 && pg.maxkp / (slices * 2) >= 2048) slices *= 2;
         k_ex_samples<<<nPairs, 1024, pg.rngCount, st>>>(pg, pb, pair0);
         k_ex_solve<<<dim3(chunks, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, 0, pg.maxIters);
         k_ex_score<<<dim3(chunks, slices, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, 0, pg.maxIters, t32);
@@ -776,7 +777,7 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
             const int n = std::min(wn, pg.maxIters - w0);
             const int chunks = (n + kRansacGroups - 1) / kRansacGroups;
             int slices = 1;
-            while (slices < 64 && (long long)chunks * nPairs * slices < 148 * 4 && pg.maxkp / (slices * 2) >= 512) slices *= 2;
+            while (slices < 64 && (long long)chunks * nPairs * slices < (long long)pg.numSms * 4 && pg.maxkp / (slices * 2) >= 512) slices *= 2;
             k_ex_solve<<<dim3(chunks, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, w0, n);
             k_ex_score<<<dim3(chunks, slices, nPairs), kRansacThreads, 0, st>>>(pg, pb, pair0, w0, n, t32);
             k_ex_replay<<<(nPairs + 31) / 32, 32, 0, st>>>(pg, pb, pair0, nPairs, w0, n);
@@ -790,7 +791,7 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
         // few pairs with many correspondences: a cluster of CTAs per pair shares the scoring (DSMEM count reduction)
         int csize = 1;
         if (pg.maxkp >= 4096 && getenv("DVO_NO_CLUSTER") == nullptr) {
-            while (csize < 8 && nPairs * csize * 2 <= 148) csize *= 2;
+            while (csize < 8 && nPairs * csize * 2 <= pg.numSms) csize *= 2;
         }
         if (csize > 1) {
             cudaLaunchConfig_t cfg{};
@@ -803,7 +804,10 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
             attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, k_ransac<true>, pg, pb, ps, pair0, t32);
+            if (cudaLaunchKernelEx(&cfg, k_ransac<true>, pg, pb, ps, pair0, t32) != cudaSuccess) {
+                (void)cudaGetLastError();      // the cluster launch was refused (resources): the single-CTA kernel does the same work
+                k_ransac<false><<<nPairs, kRansacThreads, 0, st>>>(pg, pb, ps, pair0, t32);
+            }
         } else {
             k_ransac<false><<<nPairs, kRansacThreads, 0, st>>>(pg, pb, ps, pair0, t32);
         }
@@ -816,7 +820,7 @@ void launch_ransac_pose(const OrbGeom& og, const OrbBuffers& ob, const PairGeom&
     debug_sync("k_pose_final", st);
 }
 
-void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+void launch_match(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
                   int nPairs, const double* K, cudaStream_t st) {
     if (nPairs <= 0) return;
     const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
@@ -836,6 +840,12 @@ void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, c
     { ProfScope ps_(PF_SORT, st); k_match_sort<<<nPairs, 1024, pg.sortCap * sizeof(uint32_t), st>>>(og, ob, pg, pb, slotA0, pair0, fx, fy, cx, cy); }
     g_pair_launches += pg.nnTensor ? 3 : 2;      // (k_expand_desc + k_nn_tensor | k_nn) + k_match_sort
     debug_sync("k_nn+sort", st);
+}
+
+void launch_pairs(const OrbGeom& og, const OrbBuffers& ob, const PairGeom& pg, const PairBuffers& pb, int slotA0, int pair0,
+                  int nPairs, const double* K, cudaStream_t st) {
+    if (nPairs <= 0) return;
+    launch_match(og, ob, pg, pb, slotA0, pair0, nPairs, K, st);
     launch_ransac_pose(og, ob, pg, pb, slotA0, pair0, nPairs, K, st);
 }
 

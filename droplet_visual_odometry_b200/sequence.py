@@ -150,8 +150,15 @@ class SequenceRunner:
         self.ctx = Context(width, height, nfeatures=nfeatures, max_frames=batch + 1, matcher=matcher, device=device, **kw)
 
     def run(self, frames):
-        """frames: (n, H, W) uint8 cuda tensor / host tensor / ndarray -> (n-1,) POSE_DTYPE."""
-        return self.ctx.sequence(frames, self.K)
+        """frames: (n, H, W) uint8 cuda tensor / host tensor / ndarray -> (n-1,) POSE_DTYPE.  Raises when a frame's keypoint set
+        had to be truncated (dvo_pose.frame_flags): a trajectory built on features cv2 would not return is not written."""
+        rec = self.ctx.sequence(frames, self.K)
+        bad = np.flatnonzero(rec["frame_flags"])
+        if len(bad):
+            from ._native import DvoError, describe_frame_flags
+            raise DvoError("DVO_E_CAPACITY: %d frame pair(s) (first: %d) used a truncated keypoint set (%s)"
+                           % (len(bad), int(bad[0]), describe_frame_flags(int(rec["frame_flags"][bad[0]]))))
+        return rec
 
     def block_fn(self, frames):
         """compute_block for run_sharded over a frame container indexable by slice (frames[a:b])."""

@@ -154,6 +154,19 @@ def render_frame(pose: CameraPose, width: int, height: int, texture: torch.Tenso
     return val.round().clamp_(0, 255).to(torch.uint8)
 
 
+def marker_corners(pose: CameraPose, width: int, height: int, marker_length: float = 0.4, centre=(0.3, -0.2, 10.0)) -> np.ndarray:
+    """Pixel coordinates (4, 2) float64 of the corners of a square fiducial of side ``marker_length`` on the back wall, in the
+    order a STag detector reports them (clockwise from top-left): the input get_scaling_factor_from_triangulation expects
+    (/root/reference/scripts/traj_eval_ground_truth.py:303-311 hands such (n, 2) arrays to visual_odometry_calculations)."""
+    K = camera_matrix(width, height)
+    h = marker_length / 2.0
+    cx, cy, cz = centre
+    world = np.array([[cx - h, cy - h, cz], [cx + h, cy - h, cz], [cx + h, cy + h, cz], [cx - h, cy + h, cz]], dtype=np.float64)
+    cam = (pose.R @ (world - pose.C).T).T
+    uv = (K @ cam.T).T
+    return uv[:, :2] / uv[:, 2:3]
+
+
 def render_sequence(n_frames: int, width: int = 1280, height: int = 1024, device="cpu", period: int = 48,
                     seed: int = TEXTURE_SEED, texture_size: int = TEXTURE_SIZE, start_index: int = 0):
     """Returns (frames u8 (n, H, W) tensor on ``device``, poses, K)."""

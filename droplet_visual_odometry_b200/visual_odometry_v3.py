@@ -70,6 +70,9 @@ class PairEngine:
 
     def _collect(self, K, fa=None, fb=None):
         pose = self.ctx.poses(0, 1)[0]
+        if pose["frame_flags"]:
+            raise _native.DvoError("DVO_E_CAPACITY: a frame of this pair holds a truncated keypoint set (%s)"
+                                   % _native.describe_frame_flags(int(pose["frame_flags"])))
         arr = self.ctx.pair_arrays(0, pose["n_matches"])
         out = {"status": int(pose["status"]), "E": pose["E"].reshape(3, 3).copy(), "R": pose["R"].reshape(3, 3).copy(),
                "t": pose["t"].reshape(3, 1).copy(), "good": int(pose["n_good"]), "n_inliers": int(pose["n_inliers"]),
@@ -96,9 +99,96 @@ class PairEngine:
         c.pairs(0, 0, 1, K)
         return self._collect(K)
 
+    def match_only(self, pt_prev, desc_prev, pt_cur, desc_cur, K):
+        """bf.match + sorted + KeyPoint_convert (dvo_match): no RANSAC, no pose.  The correspondences stay in pair slot 0
+        so that pose_of_last_match() can run findEssentialMat + recoverPose on them without another upload."""
+        c = self.ctx
+        c.set_features(0, pt_prev, desc_prev)
+        c.set_features(1, pt_cur, desc_cur)
+        c.match(0, 0, 1, K)
+        n = c.match_count(0)
+        arr = c.pair_arrays(0, n)
+        return {"matches": arr["matches"], "p_prev": arr["p_prev"], "p_cur": arr["p_cur"]}
+
+    def pose_of_last_match(self, K):
+        self.ctx.pose(0, 0, 1, K)
+        return self._collect(K)
+
     def pose_from_points(self, p_prev, p_cur, K):
         self.ctx.pose_points(p_prev, p_cur, K, 0)
         return self._collect(K)
+
+
+NORM_HAMMING = 6     # cv.NORM_HAMMING
+
+
+class OrbFeatureDetector:
+    """What ``VisualOdometry.feature_detector`` is in the reference: the object ``cv.ORB_create()`` returns
+    (visual_odometry_v3.py:96), reduced to the one call the reference makes on it (:373) plus the getters of the parameters
+    this build fixes.  The work runs in libdvo."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def detectAndCompute(self, image, mask=None):
+        if mask is not None:
+            raise NotImplementedError("detectAndCompute with a mask is not on the reference's path (it passes None, :373)")
+        kps, desc, _ = self._owner.compute_current_image_elements(image)
+        return kps, desc
+
+    def getMaxFeatures(self):
+        return self._owner.nfeatures
+
+    def getScaleFactor(self):
+        return 1.2000000476837158
+
+    def getNLevels(self):
+        return 8
+
+    def getEdgeThreshold(self):
+        return 31
+
+    def getFirstLevel(self):
+        return 0
+
+    def getWTA_K(self):
+        return 2
+
+    def getScoreType(self):
+        return 0      # cv.ORB_HARRIS_SCORE
+
+    def getPatchSize(self):
+        return 31
+
+    def getFastThreshold(self):
+        return 20
+
+    def descriptorSize(self):
+        return 32
+
+    def defaultNorm(self):
+        return NORM_HAMMING
+
+
+class BruteForceMatcher:
+    """What ``VisualOdometry.bf`` is in the reference: ``cv.BFMatcher(normType=NORM_HAMMING, crossCheck=True)`` (:75), with the
+    one method the ORB path calls on it (``match``, :219).  Matches come back in cv2's order (by queryIdx)."""
+
+    def __init__(self, owner, norm_type, cross_check):
+        self._owner, self.normType, self.crossCheck = owner, norm_type, cross_check
+
+    def match(self, queryDescriptors, trainDescriptors):
+        q = np.ascontiguousarray(queryDescriptors, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(trainDescriptors, dtype=np.uint8).reshape(-1, 32)
+        eng = self._owner._engine_for_descriptors(max(len(q), len(t)))
+        res = eng.match_only(np.zeros((len(q), 2), np.float32), q, np.zeros((len(t), 2), np.float32), t, np.eye(3))
+        m = res["matches"]
+        m = m[np.argsort(m[:, 0], kind="stable")]
+        return [DMatch(a, b, d) for a, b, d in m]
+
+    def knnMatch(self, queryDescriptors, trainDescriptors, k=2):
+        raise NotImplementedError("knnMatch belongs to the float-descriptor modes (:203-215); the k=2 ratio matcher of BASELINE "
+                                  "configs[3] is the context option matcher=DVO_MATCH_KNN_RATIO")
 
 
 class VisualOdometry:
@@ -136,6 +226,9 @@ class VisualOdometry:
             raise NotImplementedError("only mode='orb' is on the accelerated hot path (SIFT/SURF/FLANN: visual_odometry_v3.py:99-106)")
         self.nfeatures = int(nfeatures)
         self.device = int(device)
+        # reference :70, :75 -- the detector / matcher objects and their parameters are public attributes
+        self.feature_detector, self.norm_type, self.cross_check = self.return_feature_matching_parameters(mode)
+        self.bf = BruteForceMatcher(self, self.norm_type, self.cross_check)
         self._engine = None                     # created on first image (frame size known then)
         self._engine_size = None
         _native.load_library()                  # fail now, loudly, if the CUDA library is missing
@@ -150,6 +243,21 @@ class VisualOdometry:
         self.robot_curr_position = self.make_transform_mat(translation=self.starting_translation, euler=self.starting_euler)
 
     # ------------------------------------------------------------------ utilities (reference :93-166)
+    def return_feature_matching_parameters(self, mode):       # reference :93-107
+        if mode.lower() == "orb":
+            return OrbFeatureDetector(self), NORM_HAMMING, True
+        raise NotImplementedError("only mode='orb' is on the accelerated hot path (SIFT/SURF/FLANN: visual_odometry_v3.py:99-106)")
+
+    def _engine_for_descriptors(self, n):
+        """Engine for descriptor-only work (bf.match before any image was seen, or on more rows than the image engine holds)."""
+        if self._engine is not None and n <= self._engine.ctx.max_keypoints:
+            return self._engine
+        eng = getattr(self, "_desc_engine", None)
+        if eng is None or n > eng.ctx.max_keypoints:
+            eng = PairEngine(256, 256, nfeatures=max(int(n), 500), device=self.device)
+            self._desc_engine = eng
+        return eng
+
     def _engine_for(self, height, width):
         if self._engine is None or self._engine_size != (height, width):
             self._engine = PairEngine(width, height, nfeatures=self.nfeatures, device=self.device)
@@ -213,42 +321,43 @@ class VisualOdometry:
         """reference :191-239 (ORB branch, intended semantics)."""
         if self._engine is None:
             raise _native.DvoError("no frame has been processed yet: frame size unknown")
-        res = self._engine.match_and_pose(keypoints_to_array(previous_key_points), previous_descriptors,
-                                          keypoints_to_array(current_key_points), current_descriptors, self.intrinsic_coefficient_matrix)
+        res = self._engine.match_only(keypoints_to_array(previous_key_points), previous_descriptors,
+                                      keypoints_to_array(current_key_points), current_descriptors, self.intrinsic_coefficient_matrix)
         m = res["matches"]
         matches = [DMatch(q, t, d) for q, t, d in m]
         top_prev = [previous_key_points[q] for q in m[:, 0]]
         top_cur = [current_key_points[t] for t in m[:, 1]]
-        self._pending_pair = res    # same correspondences will be asked for a pose next; keep the device result
+        self._pending_match = res   # the same correspondences will be asked for a pose next: they are already on the device
         return matches, top_prev, top_cur
 
     def get_scaling_factor_from_triangulation(self, current_projection_matrix, previous_marker_corners, current_marker_corners):
-        """reference :263-291: distance between the first two triangulated marker corners (cv.triangulatePoints is a
-        per-point 4x4 DLT null vector; four points, host numpy)."""
+        """reference :263-291: cv.triangulatePoints on the fiducial corners of the two frames, then the distance between the
+        first two triangulated corners measured on the RAW homogeneous vectors (no division by w, :272-279).  The vectors
+        come from libdvo's restatement of OpenCV's DLT + Jacobi SVD (dvo_triangulate_points_host), which reproduces cv2's
+        null-vector sign: with the opposite sign for one of the two points the 'distance' becomes |X0 + X1|."""
         self.projection_matrix_list.append(self.previous_projection_matrix)
-        P0, P1 = np.asarray(self.previous_projection_matrix, float), np.asarray(current_projection_matrix, float)
-        a = np.asarray(previous_marker_corners, dtype=np.float64).reshape(-1, 2)
-        b = np.asarray(current_marker_corners, dtype=np.float64).reshape(-1, 2)
-        X = np.empty((4, len(a)))
-        for i in range(len(a)):
-            A = np.stack([a[i, 0] * P0[2] - P0[0], a[i, 1] * P0[2] - P0[1], b[i, 0] * P1[2] - P1[0], b[i, 1] * P1[2] - P1[1]])
-            X[:, i] = np.linalg.svd(A)[2][3]
-        # the reference measures the distance on the raw homogeneous coordinates (no division by w), :272-279
-        return math.sqrt((X[0, 0] - X[0, 1]) ** 2 + (X[1, 0] - X[1, 1]) ** 2 + (X[2, 0] - X[2, 1]) ** 2)
+        a = np.asarray(previous_marker_corners)
+        b = np.asarray(current_marker_corners)
+        marker_corners_4D = _native.triangulate_points(self.previous_projection_matrix, current_projection_matrix,
+                                                       a.reshape(-1, 2), b.reshape(-1, 2))
+        if a.dtype == np.float32:       # cv2 returns points4D in the type of projPoints1
+            marker_corners_4D = marker_corners_4D.astype(np.float32)
+        marker_Xs, marker_Ys, marker_Zs = marker_corners_4D[0, :], marker_corners_4D[1, :], marker_corners_4D[2, :]
+        return math.sqrt((marker_Xs[0] - marker_Xs[1]) ** 2 + (marker_Ys[0] - marker_Ys[1]) ** 2 + (marker_Zs[0] - marker_Zs[1]) ** 2)
 
     def get_transformation_between_two_frames(self, array_previous_key_points, array_current_key_points,
                                               previous_marker_corners=None, current_marker_corners=None):
         """reference :293-345."""
-        pend = getattr(self, "_pending_pair", None)
+        pend = getattr(self, "_pending_match", None)
+        self._pending_match = None
         if pend is not None and len(pend["p_prev"]) == len(array_previous_key_points) and \
                 np.array_equal(pend["p_prev"], np.asarray(array_previous_key_points, np.float32).reshape(-1, 2)) and \
                 np.array_equal(pend["p_cur"], np.asarray(array_current_key_points, np.float32).reshape(-1, 2)):
-            res = pend
+            res = self._engine.pose_of_last_match(self.intrinsic_coefficient_matrix)
         else:
             h, w = self._engine_size if self._engine_size else (self.frame_height, self.frame_width)
             res = self._engine_for(h, w).pose_from_points(array_previous_key_points, array_current_key_points,
                                                           self.intrinsic_coefficient_matrix)
-        self._pending_pair = None
         return self._finish_pair(res, previous_marker_corners, current_marker_corners)
 
     def _finish_pair(self, res, previous_marker_corners, current_marker_corners):

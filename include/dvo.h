@@ -40,6 +40,11 @@ extern "C" {
 #define DVO_PAIR_TOO_FEW_MATCHES 1 /* < 5 correspondences: cv.findEssentialMat returns None */
 #define DVO_PAIR_NO_MODEL 2        /* RANSAC found no model with > 4 inliers                */
 
+/* per-frame flags: cv2 keeps every tie at a retainBest boundary, the context has room for quota + 64 per level */
+#define DVO_FRAME_TIES_TRUNCATED 1        /* more Harris-boundary ties than a level can hold: keypoint set != cv2's */
+#define DVO_FRAME_CANDIDATES_TRUNCATED 2  /* FAST survivor list of a level overflowed (cannot happen with 3x3 NMS)  */
+#define DVO_FRAME_KEYPOINTS_TRUNCATED 4   /* more keypoints than dvo_max_keypoints                                  */
+
 typedef struct dvo_ctx dvo_ctx;
 
 typedef struct dvo_config {
@@ -62,7 +67,8 @@ typedef struct dvo_config {
                                 is solved and scored (whole-GPU batched solve + Sampson sweep; BASELINE configs[4] "all
                                 hypotheses scored"); the first model with the highest inlier count wins                */
     int nn_engine;           /* cross-check matcher: 0 (default) int8 tensor-core GEMM (tcgen05, 256 - 2*hamming = dot of +-1 bytes);
-                                1: XOR + POPC kernel.  Both give cv2's matches bit for bit.  The ratio matcher always uses 1 */
+                                1: XOR + POPC kernel (k_nn).  Both give cv2's matches bit for bit, and both serve either matcher: the ratio
+                                matcher (DVO_MATCH_KNN_RATIO) keeps the runner-up per row on whichever engine is selected */
 } dvo_config;
 
 /* Result of one frame pair: what cv.findEssentialMat + cv.recoverPose return (visual_odometry_v3.py:297-306). */
@@ -78,7 +84,7 @@ typedef struct dvo_pose {
     int32_t best_iter;       /* iteration that produced E                   */
     int32_t candidate;       /* 0..3: which (R1|R2, +-t) recoverPose chose   */
     int32_t n_prev, n_cur;   /* keypoints in the two frames                 */
-    int32_t reserved;
+    int32_t frame_flags;     /* DVO_FRAME_* bits of the pair's two frames, OR-ed: non-zero = a feature set was truncated */
 } dvo_pose;
 
 /* Device-side views of one frame's features: cv2 detectAndCompute output (visual_odometry_v3.py:373). */
@@ -130,6 +136,11 @@ int dvo_set_undistort(dvo_ctx* ctx, const double* K, const double* dist, int n_d
  * (visual_odometry_v3.py:373, called from compute_current_image_elements :370-379). */
 int dvo_orb(dvo_ctx* ctx, int slot0, int n, void* stream);
 
+/* DVO_FRAME_* flags of slots [slot0, slot0+n) after dvo_orb (host destination, synchronises).  A non-zero flag means the
+ * slot's keypoint set is NOT what cv2 returns (truncated); callers must treat it as DVO_E_CAPACITY.  The same bits ride in
+ * dvo_pose.frame_flags for the sequence runner. */
+int dvo_get_frame_flags(dvo_ctx* ctx, int slot0, int n, int32_t* h_flags, void* stream);
+
 /* Copy one slot's features into caller device buffers (async on stream). */
 int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stream);
 
@@ -137,6 +148,16 @@ int dvo_get_features(dvo_ctx* ctx, int slot, const dvo_features* out, void* stre
  * sorted (:219-221), cv.KeyPoint_convert (:355,:358), cv.findEssentialMat (:297-300), cv.recoverPose (:303-306).
  * K is the 3x3 row-major camera matrix (host pointer, read before the call returns). */
 int dvo_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream);
+
+/* The two halves of dvo_pairs as separate calls, for callers that use the reference's method-level surface.
+ * dvo_match: bf.match + sorted (:219-221) + cv.KeyPoint_convert (:355,:358) only -- what get_matches_between_two_frames
+ * (:191-239) does -- leaving the sorted (queryIdx, trainIdx, distance) list and the matched coordinates in pair slots
+ * [pair0, pair0+n) (read them with dvo_get_match_count + dvo_get_pair_arrays); no RANSAC runs.
+ * dvo_pose_pairs: cv.findEssentialMat + cv.recoverPose (:297-306) on the correspondences already in those pair slots (from
+ * dvo_match); slot0 names the frame slots the pairs came from (keypoint counts of the record) or -1. */
+int dvo_match(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream);
+int dvo_pose_pairs(dvo_ctx* ctx, int slot0, int pair0, int n, const double* K, void* stream);
+int dvo_get_match_count(dvo_ctx* ctx, int pair, int* h_count /*host, synchronises*/, void* stream);
 
 /* Overwrite one slot's keypoint coordinates and descriptors with caller data (kind 0 device, 1 host source;
  * synchronises): lets get_matches_between_two_frames (:191-239) run on caller-supplied descriptors. */
@@ -151,6 +172,13 @@ int dvo_pose_points(dvo_ctx* ctx, int pair, const float* pts_prev, const float* 
 /* Copy n pair results (device->device or device->host, async on stream). kind: 0 device dst, 1 host dst. */
 int dvo_get_poses(dvo_ctx* ctx, int pair0, int n, dvo_pose* dst, int kind, void* stream);
 int dvo_get_pair_arrays(dvo_ctx* ctx, int pair, const dvo_pair_arrays* out, void* stream);
+
+/* cv.triangulatePoints(projMatr1, projMatr2, projPoints1, projPoints2) as get_scaling_factor_from_triangulation calls it
+ * (visual_odometry_v3.py:263-291) on the fiducial corners of two frames.  Host arithmetic (four points per pair; no
+ * context, no device work): P0, P1 are 3x4 row-major projection matrices, pts0/pts1 are n x 2, X receives the 4 x n
+ * homogeneous points row-major, UNNORMALISED and with cv2's sign (the last row of cv::SVD's Vt): the reference measures
+ * the marker edge on these raw vectors (:272-279), so the sign convention is part of the contract. */
+int dvo_triangulate_points_host(const double* P0, const double* P1, const double* pts0, const double* pts1, int n, double* X);
 
 /* Whole-sequence runner: consecutive-pair VO over n_frames frames; writes n_frames-1 dvo_pose records.
  * Frames are processed in batches of max_frames-1 with a one-frame carry, each frame's ORB computed once.

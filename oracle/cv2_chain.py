@@ -106,3 +106,27 @@ def frame_pair(img_prev: np.ndarray, img_cur: np.ndarray, K: np.ndarray, nfeatur
     res = pose_from_points(p_prev, p_cur, np.asarray(K, dtype=np.float64))
     res.update(matches=m, p_prev=p_prev, p_cur=p_cur, feats_prev=fa, feats_cur=fb)
     return res
+
+
+def marker_scaled_transform(R, t, K, prev_projection, prev_corners, cur_corners, real_marker_length):
+    """The tail of get_transformation_between_two_frames, /root/reference/scripts/visual_odometry_v3.py:309-345, call for call:
+    P = K [R|t] (:309), cv.triangulatePoints on the fiducial corners (:265), distance of the first two RAW homogeneous
+    points (:272-279), t *= real_marker_length / distance (:321-325), euler_from_matrix(R, 'rxyz') (:334) fed to
+    euler_matrix(..., 'sxyz') (:140) behind translation_matrix(t) (:141-142).  The two Gohlke conventions are taken from
+    scipy.spatial.transform.Rotation (rotating xyz = intrinsic 'XYZ', static xyz = extrinsic 'xyz').
+    Returns (4x4 prev_to_curr, current projection matrix, measured distance)."""
+    from scipy.spatial.transform import Rotation
+    K = np.asarray(K, dtype=np.float64)
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    t = np.asarray(t, dtype=np.float64).reshape(3, 1)
+    P = K.dot(np.hstack((R, t)))
+    X = cv.triangulatePoints(projMatr1=np.asarray(prev_projection, dtype=np.float64), projMatr2=P,
+                             projPoints1=np.asarray(prev_corners).T, projPoints2=np.asarray(cur_corners).T)
+    d = float(np.sqrt((X[0, 0] - X[0, 1]) ** 2 + (X[1, 0] - X[1, 1]) ** 2 + (X[2, 0] - X[2, 1]) ** 2))
+    ts = t[:, 0] * (real_marker_length / d)
+    e = Rotation.from_matrix(R).as_euler("XYZ")
+    M = np.eye(4)
+    M[:3, :3] = Rotation.from_euler("xyz", e).as_matrix()
+    T = np.eye(4)
+    T[:3, 3] = ts
+    return T.dot(M), P, d

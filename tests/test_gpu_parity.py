@@ -553,3 +553,57 @@ def test_tensor_core_matcher_large_keypoint_sets(env):
         got.append((int(p["n_matches"]), ctx.pair_arrays(0, p["n_matches"])["matches"]))
         ctx.close()
     assert got[0][0] == got[1][0] == nb and np.array_equal(got[0][1], got[1][1])
+
+
+# ----------------------------------------------------------------------------------------------- capacity is never silent
+def _blobs(w, h, pitch, off=40):
+    """identical 3x3 blobs with a brighter centre: every centre is a FAST corner that survives NMS, and all of them share one
+    FAST score and one Harris response"""
+    img = np.full((h, w), 40, np.uint8)
+    for y in range(off, h - off, pitch):
+        for x in range(off, w - off, pitch):
+            img[y - 1:y + 2, x - 1:x + 2] = 120
+            img[y, x] = 220
+    return img
+
+
+def test_tie_overflow_fails_loudly_and_mild_ties_equal_cv2(env):
+    """cv2's retainBest keeps EVERY tie at the boundary.  A periodic pattern gives thousands of keypoints with
+    identical FAST scores and Harris responses: more than quota + 64 per level cannot be held, and then every reader must
+    fail (DVO_E_CAPACITY) instead of returning a truncated set with status OK.  With few enough ties the set equals cv2's."""
+    import cv2
+    nf, w, h = 500, 640, 480
+    ctx = env.native.Context(w, h, nfeatures=nf, max_frames=3)
+    dense = _blobs(w, h, 12)      # 1598 level-0 keypoints with one response: cv2 keeps them all (1970 in total)
+    n_cv = len(cv2.ORB_create(nfeatures=nf).detect(dense, None))
+    assert n_cv > ctx.max_keypoints, "the pattern must overflow: cv2 keeps %d keypoints, capacity %d" % (n_cv, ctx.max_keypoints)
+    ctx.load_frames(np.stack([dense, dense]), 0)
+    ctx.orb(0, 2)
+    flags = ctx.frame_flags(0, 2)
+    assert (flags & env.native.FRAME_TIES_TRUNCATED).all(), flags
+    with pytest.raises(env.native.DvoError, match="DVO_E_CAPACITY"):
+        ctx.features(0)
+    ctx.pairs(0, 0, 1, env.K)
+    assert ctx.poses(0, 1)[0]["frame_flags"] != 0
+    rec = ctx.sequence(np.stack([dense, dense, dense]), env.K)
+    assert (rec["frame_flags"] != 0).all()
+    from droplet_visual_odometry_b200.sequence import SequenceRunner
+    from droplet_visual_odometry_b200.visual_odometry_v3 import VisualOdometry
+    with pytest.raises(env.native.DvoError, match="DVO_E_CAPACITY"):
+        SequenceRunner(w, h, env.K, nfeatures=nf, batch=2).run(np.stack([dense, dense, dense]))
+    vo = VisualOdometry(mode="orb", camera_matrix=env.K, nfeatures=nf)
+    with pytest.raises(env.native.DvoError, match="DVO_E_CAPACITY"):
+        vo.visual_odometry_calculations(dense, dense, np.eye(4))
+    with pytest.raises(env.native.DvoError, match="DVO_E_CAPACITY"):
+        vo.compute_current_image_elements(dense)
+    # fewer blobs: 140 tied keypoints at level 0 against a quota of 109 -- cv2 keeps all of them (531 > nfeatures in total) and
+    # so must we, in cv2's order, with the flags clear
+    mild = _blobs(w, h, 40)
+    ctx.load_frames(mild[None], 0)
+    ctx.orb(0, 1)
+    assert ctx.frame_flags(0, 1)[0] == 0
+    f, ref = ctx.features(0), env.chain.orb_features(mild, nf)
+    assert len(ref["pt"]) > nf and len(f["pt"]) == len(ref["pt"])
+    for k in ("pt", "angle", "response", "octave", "desc"):
+        assert np.array_equal(f[k], ref[k]), k
+    ctx.close()
