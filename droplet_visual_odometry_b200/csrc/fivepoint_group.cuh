@@ -75,9 +75,35 @@ __device__ int five_point_solve_group(const double* x1, const double* x2, SolveS
             Mr[c] -= dot * vk[k];
         }
     }
+    // cv2's basis of that null space (see null_space_5x9 in mathcore.cuh): Gram-Schmidt of cv::SVD's fixed +-1/9 fill-in
+    // vectors, done on the four trailing coordinates of H^T s_i (lanes 5..8), then rotated back with H.
+    double u[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        double e = (gl == 5 + b) ? 1.0 : 0.0;
+        double e = gl < 9 ? cv_svd_fill_component(b, gl) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double dot = gsum(gmask, vk[k] * e) * beta[k];
+            e -= dot * vk[k];
+        }
+        u[b] = (gl >= 5 && gl < 9) ? e : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= b) continue;
+                const double sd = gsum(gmask, u[b] * u[j]);
+                u[b] -= sd * u[j];
+            }
+        const double nn = gsum(gmask, u[b] * u[b]);
+        u[b] *= nn > 0 ? 1.0 / sqrt(nn) : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double e = u[b];
 #pragma unroll
         for (int k = 4; k >= 0; --k) {
             const double dot = gsum(gmask, vk[k] * e) * beta[k];

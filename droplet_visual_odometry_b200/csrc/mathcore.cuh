@@ -286,6 +286,16 @@ DVO_HD bool sampson_inlier(const double* E, double x1, double y1, double x2, dou
     return (float)(num / den) <= t32;
 }
 
+// cv.findEssentialMat's K-normalisation, bit for bit: OpenCV evaluates `(points.col(0) - cx) / fx` as the matrix expression
+// alpha * p + beta with alpha = 1 / fx and beta = -cx * alpha, and its convertTo kernel (AVX2/FMA3 dispatch) fuses the
+// multiply-add.  (p - cx) / fx differs from that in the last bit for most points, and a 1-ulp change of the normalised
+// coordinates is enough to change the RANSAC winner on ~2 % of real frame pairs (ill-conditioned minimal samples).
+// Verified against cv2 4.13.0: 120 of 120 five-point calls bit-identical with this form, 0 of 120 with any other.
+DVO_HD double cv_normalize_coord(float p, double f, double c) {
+    const double alpha = 1.0 / f;
+    return fma((double)p, alpha, -(c * alpha));
+}
+
 // ---- small dense linear algebra ------------------------------------------------------------------------------------
 // One-sided (Hestenes) Jacobi on the columns of an NxN matrix A (row-major, overwritten by U*Sigma); V accumulates the
 // right singular vectors as columns.
@@ -532,7 +542,21 @@ DVO_HD void poly_mul21(const double* a10, const double* b, double* out20, double
         for (int j = 0; j < 4; ++j) out20[cubic_index(i, j)] += sign * a10[i] * b[j];
 }
 
-// Orthonormal basis of the null space of the 5x9 constraint matrix: Householder QR of its transpose.
+// Null-space basis of the 5x9 epipolar constraint matrix -- THE basis cv2's solver works in, which matters: the hidden-
+// variable polynomial built from it is ill-conditioned for coplanar / clustered minimal samples, and how its roots move
+// under rounding depends on the basis.  With any other orthonormal basis of the same null space (the Householder columns
+// this code used before) 18 % of the minimal samples of a real sequence gave inlier counts different from cv2's; with
+// cv2's basis 6 % do (the rest is rounding noise on samples where cv2 disagrees with itself under a 1-ulp change).
+//
+// cv2 runs cv::SVD::compute(Q, w, u, vt, FULL_UV) and takes rows 5..8 of vt (five-point.cpp).  Q has 5 rows, so those rows
+// belong to no singular value: cv::SVD's Jacobi path fills them by Gram-Schmidt -- row i starts as the vector of +-1/9
+// whose signs are bit 8 of successive draws of cv::RNG(0x12345678), is orthogonalised (twice) against every earlier row
+// and normalised.  Mathematically: b_i = normalise(P s_i - sum_{j<i} (P s_i . b_j) b_j) with P the projector on the null
+// space.  Here: Householder QR of Q^T gives H with H^T (null space) = span(e5..e8); the Gram-Schmidt runs on the four
+// trailing coordinates of H^T s_i and the result is rotated back.
+constexpr unsigned long long kCvSvdFillSigns = 0x74ec6fb84ull;   // bit (9 i + k): sign of component k of s_i is +
+DVO_HD double cv_svd_fill_component(int i, int k) { return ((kCvSvdFillSigns >> (9 * i + k)) & 1ull) ? (1.0 / 9.0) : -(1.0 / 9.0); }
+
 // basis[k*9 + c], k = 0..3.
 DVO_HDN void null_space_5x9(const double* Q /*5x9*/, double* basis /*4x9*/) {
     double M[9 * 5];   // M = Q^T, column-major by constraint: M[r*5 + c]
@@ -558,10 +582,36 @@ DVO_HDN void null_space_5x9(const double* Q /*5x9*/, double* basis /*4x9*/) {
             for (int r = k; r < 9; ++r) M[r * 5 + c] -= dot * vs[k][r];
         }
     }
-    // columns 5..8 of H1 H2 ... H5
+    // trailing coordinates of H^T s_i = H5 ... H1 s_i
+    double u[4][4];
     for (int b = 0; b < 4; ++b) {
         double e[9];
-        for (int r = 0; r < 9; ++r) e[r] = (r == 5 + b) ? 1.0 : 0.0;
+        for (int r = 0; r < 9; ++r) e[r] = cv_svd_fill_component(b, r);
+        for (int k = 0; k < 5; ++k) {
+            double dot = 0;
+            for (int r = k; r < 9; ++r) dot += vs[k][r] * e[r];
+            dot *= betas[k];
+            for (int r = k; r < 9; ++r) e[r] -= dot * vs[k][r];
+        }
+        for (int r = 0; r < 4; ++r) u[b][r] = e[5 + r];
+    }
+    // Gram-Schmidt (two passes, as cv::SVD does) and normalisation
+    for (int b = 0; b < 4; ++b) {
+        for (int pass = 0; pass < 2; ++pass)
+            for (int j = 0; j < b; ++j) {
+                double sd = 0;
+                for (int r = 0; r < 4; ++r) sd += u[b][r] * u[j][r];
+                for (int r = 0; r < 4; ++r) u[b][r] -= sd * u[j][r];
+            }
+        double nn = 0;
+        for (int r = 0; r < 4; ++r) nn += u[b][r] * u[b][r];
+        nn = nn > 0 ? 1.0 / sqrt(nn) : 0.0;
+        for (int r = 0; r < 4; ++r) u[b][r] *= nn;
+    }
+    // back: b_i = H1 ... H5 [0; u_i]
+    for (int b = 0; b < 4; ++b) {
+        double e[9];
+        for (int r = 0; r < 9; ++r) e[r] = r >= 5 ? u[b][r - 5] : 0.0;
         for (int k = 4; k >= 0; --k) {
             double dot = 0;
             for (int r = k; r < 9; ++r) dot += vs[k][r] * e[r];

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(1024) k_match_sort(OrbGeom og, OrbBuffers ob, 
         pb.ptsPrev[(o + r) * 2] = ax; pb.ptsPrev[(o + r) * 2 + 1] = ay;
         pb.ptsCur[(o + r) * 2] = bx; pb.ptsCur[(o + r) * 2 + 1] = by;
         double* np_ = pb.normPts + (o + r) * 4;
-        np_[0] = ((double)ax - cx) / fx; np_[1] = ((double)ay - cy) / fy;
-        np_[2] = ((double)bx - cx) / fx; np_[3] = ((double)by - cy) / fy;
+        np_[0] = cv_normalize_coord(ax, fx, cx); np_[1] = cv_normalize_coord(ay, fy, cy);
+        np_[2] = cv_normalize_coord(bx, fx, cx); np_[3] = cv_normalize_coord(by, fy, cy);
     }
     if (tid == 0) {
         int* rs = pb.ransacState + pair * 8;
@@ -730,8 +730,8 @@ __global__ void __launch_bounds__(256) k_points_prep(PairGeom pg, PairBuffers pb
         float ax = pb.ptsPrev[(o + r) * 2], ay = pb.ptsPrev[(o + r) * 2 + 1];
         float bx = pb.ptsCur[(o + r) * 2], by = pb.ptsCur[(o + r) * 2 + 1];
         double* np_ = pb.normPts + (o + r) * 4;
-        np_[0] = ((double)ax - cx) / fx; np_[1] = ((double)ay - cy) / fy;
-        np_[2] = ((double)bx - cx) / fx; np_[3] = ((double)by - cy) / fy;
+        np_[0] = cv_normalize_coord(ax, fx, cx); np_[1] = cv_normalize_coord(ay, fy, cy);
+        np_[2] = cv_normalize_coord(bx, fx, cx); np_[3] = cv_normalize_coord(by, fy, cy);
         pb.matches[(o + r) * 3 + 0] = r; pb.matches[(o + r) * 3 + 1] = r; pb.matches[(o + r) * 3 + 2] = 0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
