@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--matcher-engine", default="tensor", choices=["tensor", "popc"],
                     help="cross-check matcher: int8 tcgen05 GEMM (default) or the XOR+POPC integer-pipe kernel (BASELINE north_star item 4 as written)")
+    ap.add_argument("--regions", type=int, default=5,
+                    help="timed regions of --steps steps each, back to back, every one bracketed by barrier + sync; the line reports the MEDIAN region "
+                         "(all of them are listed under config.region_ms)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE configs[0], [3], [4] timings (N=1 only)")
     ap.add_argument("--ingest", default="none", choices=["none", "grey", "bgr"],
                     help="widened path (SURVEY 8f row 2): frames arrive distorted (grey or BGR) and cv.cvtColor + cv.undistort "
                          "run inside the timed region on both arms; default: the BASELINE workload (undistorted mono frames)")
@@ -300,6 +304,97 @@ def _bind_to_gpu_numa_node(local):
     return None
 
 
+def other_configs(dev, with_cpu=True):
+    """BASELINE.json configs[0], [3], [4] -- parity-test cases, timed here so that the driver's line carries them: CUDA events around
+    the C-ABI calls (inputs resident) and, beside each, the cv2 chain in this process with cv2's default threading."""
+    import torch
+    from droplet_visual_odometry_b200 import synth, _native
+    from droplet_visual_odometry_b200.visual_odometry_v3 import VisualOdometry
+    from oracle import cv2_chain
+    have_cv = with_cpu and cv2_chain.available()
+    if have_cv:
+        import cv2
+        cv2.setNumThreads(-1)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def cpu_ms(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    out = {}
+    # ---- configs[0]: one 1280x1024 pair, ORB 500 (the reference's literal): stage calls on resident frames, and the per-call
+    # latency of the drop-in method with host images in and the 4x4 out
+    frames, _, K = synth.render_sequence(2, device=dev)
+    fh = frames.cpu().numpy()
+    ctx = _native.Context(1280, 1024, nfeatures=500, max_frames=2, device=dev.index)
+
+    def c0():
+        ctx.load_frames(frames, 0)
+        ctx.orb(0, 2)
+        ctx.pairs(0, 0, 1, K)
+    c = {"workload": "one 1280x1024 pair, ORB 500, crossCheck + RANSAC + recoverPose", "gpu_ms_resident": round(timed(c0, 20), 3)}
+    ctx.close()
+    vo = VisualOdometry(mode="orb", camera_matrix=K, nfeatures=500, device=dev.index)
+    T = np.eye(4)
+    vo.visual_odometry_calculations(fh[0], fh[1], T)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        vo.visual_odometry_calculations(fh[0], fh[1], T)
+    c["gpu_ms_per_call_host_images"] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
+    if have_cv:
+        c["cv2_ms"] = round(cpu_ms(lambda: cv2_chain.frame_pair(fh[0], fh[1], K, 500), 5), 2)
+        c["cv2_threads"] = int(cv2.getNumThreads())
+    out["config0_two_frame"] = c
+    del vo
+    # ---- configs[3]: 2448x2048, ORB 10000, kNN k=2 ratio + reverse check
+    frames, _, K = synth.render_sequence(5, width=2448, height=2048, device=dev)
+    ctx = _native.Context(2448, 2048, nfeatures=10000, max_frames=5, matcher=_native.DVO_MATCH_KNN_RATIO, device=dev.index)
+
+    def c3():
+        ctx.load_frames(frames, 0)
+        ctx.orb(0, 5)
+        ctx.pairs(0, 0, 4, K)
+    c = {"workload": "2448x2048, ORB 10000, knnMatch(k=2) + 0.75 ratio + reverse check, RANSAC + recoverPose; 5 frames = 4 pairs",
+         "gpu_ms_per_pair": round(timed(c3, 5) / 4, 3)}
+    c["matches_median"] = float(np.median(ctx.poses(0, 4)["n_matches"]))
+    ctx.close()
+    if have_cv:
+        fh = frames[:2].cpu().numpy()
+        c["cv2_ms_per_pair"] = round(cpu_ms(lambda: cv2_chain.frame_pair(fh[0], fh[1], K, 10000, matcher="knn"), 1), 1)
+        c["cv2_threads"] = int(cv2.getNumThreads())
+    out["config3_high_density"] = c
+    del frames
+    # ---- configs[4]: RANSAC-heavy, 40 % outliers, maxIters 4096, points only
+    sweep = {}
+    for n in (1000, 5000, 20000, 50000):
+        p1, p2, K, R, t, truth = synth.synthetic_correspondences(n, 0.4, 0.3, seed=n)
+        a_, b_ = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
+        ctx = _native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=4096, device=dev.index)
+        e = {"gpu_ms_cv2_stop_rule": round(timed(lambda: ctx.pose_points(a_, b_, K), 5), 3), "iterations": int(ctx.poses(0, 1)[0]["ransac_iters"])}
+        ctx.close()
+        ctx = _native.Context(64, 64, nfeatures=n, max_frames=2, ransac_max_iters=4096, ransac_exhaustive=True, device=dev.index)
+        e["gpu_ms_all_4096_scored"] = round(timed(lambda: ctx.pose_points(a_, b_, K), 5), 3)
+        ctx.close()
+        if have_cv:
+            e["cv2_ms"] = round(cpu_ms(lambda: cv2_chain.pose_from_points(p1, p2, K, max_iters=4096), 2), 2)
+        sweep[str(n)] = e
+    out["config4_ransac_heavy"] = {"workload": "synthetic correspondences, 40 % outliers, findEssentialMat(maxIters=4096) + recoverPose", "by_match_count": sweep}
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -349,28 +444,44 @@ def run_b200(a):
             pairs += ctx.sequence_step(frames[lo:hi], Kpose, out, first=(fresh and s == first_step))
         return pairs
 
-    # ---- warm-up (also primes the carry slot so every timed step is B pairs)
+    # ---- warm-up (also primes the carry slot so every timed step is B pairs); the path's one collective is issued here too, so
+    # that NCCL's lazy channel set-up for all-gather is not inside a timed region
+    send = poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec]
     device_pass(0, W_steps, fresh=True)
     ctx.flush()
-    barrier()
-    launches0 = ctx.kernel_launches
-    sampler = ClockSampler(local) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    npairs = device_pass(W_steps, K_steps, fresh=False)
-    ctx.flush()     # join torch's stream with the pipelined runner's internal streams before the closing event
-    if world > 1:   # the path's one exchange step: all-gather of the per-pair (R, t, status) records
-        dist.all_gather_into_tensor(gathered, poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec])
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
-    launches = ctx.kernel_launches - launches0
-    assert npairs == K_steps * B
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        for _ in range(2):
+            dist.all_gather_into_tensor(gathered, send)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    R_regions = max(a.regions, 1)
+    region_ms, gather_ms = [], []
+    npairs = 0
+    for r in range(R_regions):
+        # every region times the same K steps (3.9 GB of frames, far beyond L2).  The step before it is replayed untimed so
+        # that the carried frame is the true predecessor of the region's first frame.
+        device_pass(W_steps - 1, 1, fresh=False)
+        ctx.flush()
+        barrier()
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        launches0 = ctx.kernel_launches
+        ev0.record()
+        npairs = device_pass(W_steps, K_steps, fresh=False)
+        ctx.flush()     # join torch's stream with the pipelined runner's internal streams before the closing event
+        ev1.record()
+        launches = ctx.kernel_launches - launches0      # kernels of ONE timed region
+        if world > 1:   # the path's one exchange step: all-gather of the per-pair (R, t, status) records, on the compute stream
+            dist.all_gather_into_tensor(gathered, send)
+        ev2.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev2), ev1.elapsed_time(ev2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms.append(float(t[0].item()))
+        gather_ms.append(float(t[1].item()))
+    clocks = sampler.stop() if sampler else None
+    assert npairs == K_steps * B
+    ms = float(np.median(region_ms))
     value = world * npairs / (ms / 1e3)
     host_poses = poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec].cpu().numpy().view(POSE_DTYPE)
     ok_frac = float(np.mean(host_poses["status"] == 0))
@@ -407,6 +518,23 @@ def run_b200(a):
         e2e_s = float(t.item())
     e2e_value = world * e2e_pairs / e2e_s
 
+    # ---- what the platform allows for that: pinned host -> device copies of the same frames, nothing else, all ranks at once
+    h2d_dst = torch.empty_like(e2e_frames, device=dev)
+    h2d_dst.copy_(e2e_frames, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h2d_dst.copy_(e2e_frames, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    h2d_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([h2d_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_s = float(t.item())
+    h2d_gbs_per_rank = 3 * e2e_frames.numel() / h2d_s / 1e9
+    h2d_pairs_ceiling = world * h2d_gbs_per_rank * 1e9 / (a.width * a.height * (3 if a.ingest == "bgr" else 1))
+    del h2d_dst
+
     # ---- roofline pass: the same K steps again with per-kernel CUDA events on the launching stream
     roofline, stages = None, None
     if rank == 0:
@@ -430,6 +558,16 @@ def run_b200(a):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         stages = {}
         nkp = a.nfeatures
+        pipe = _native.measure_peaks(local)       # FP32 / FP64 (fused and unfused) / POPC / int8-tensor rates of THIS device, now
+        hp = host_poses
+        n_prev, n_cur = hp["n_prev"].astype(np.float64), hp["n_cur"].astype(np.float64)
+        nm, it = hp["n_matches"].astype(np.float64), hp["ransac_iters"].astype(np.float64)
+        # algorithmic work per timed pass (K_steps batches), SURVEY 8d: Sampson scoring 33 flop per (model, match), 4.4 models per
+        # hypothesis, ~3e4 flop per 5-point solve; recoverPose: 2 DLT triangulations per match (the other two follow by
+        # symmetry), ~3000 flop each (4x4 one-sided Jacobi, ~6 sweeps) + the cheirality tests
+        ransac_flop = float(np.sum(it * (4.4 * nm * 33.0 + 3.0e4)))
+        cheir_flop = float(np.sum(nm * 2 * 3000.0))
+        spec_iters = float(np.sum(np.ceil(it / 16.0) * 16.0))      # k_ransac solves and scores whole chunks of 16 hypotheses
         for name, (tms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             if cnt == 0:
                 continue
@@ -441,19 +579,41 @@ def run_b200(a):
                 st["achieved_GBps"] = round(bytes_total / (tms * 1e-3) / 1e9, 2)
                 st["frac_of_hbm_peak"] = round(st["achieved_GBps"] / peak, 4)
             if name == "k_nn" and a.matcher_engine == "tensor":
-                # cross-check matcher = int8 GEMM on the tensor cores (k_expand_desc + k_nn_tensor): both directions of the
-                # N x N x 256 distance matrix, 2 ops per multiply-add; peak = 2 x the measured bf16 rate (int8 runs at twice
-                # bf16 on sm_100a), else 2 x 2250 nominal
-                ops = 2.0 * 2 * nkp * nkp * 256 * B * cnt
+                # cross-check matcher = int8 GEMM on the tensor cores (k_expand_desc + k_nn_tensor).  Algorithmic work: the
+                # n_prev x n_cur x 256 distance matrix ONCE, 2 ops per multiply-add (the kernel computes it twice -- the reverse
+                # direction is the transposed product -- which is its own inefficiency, not algorithmic work).  Peak: the
+                # tcgen05.mma.kind::i8 issue rate measured by libdvo's microbenchmark on this device.
+                ops = 2.0 * float(np.sum(n_prev * n_cur)) * 256
                 st["int8_tops"] = round(ops / (tms * 1e-3) / 1e12, 1)
-                int8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
-                st["frac_of_int8_tensor_peak"] = round(st["int8_tops"] / int8_peak, 4)
-                st["int8_peak_tops"] = int8_peak
+                st["int8_peak_tops_measured"] = round(pipe["int8_tensor_ops"] / 1e12, 1)
+                st["frac_of_int8_tensor_peak"] = round(ops / (tms * 1e-3) / max(pipe["int8_tensor_ops"], 1.0), 4)
+                st["executed_over_algorithmic"] = 2.0
             if name == "k_nn" and a.matcher_engine == "popc":
-                # every distance is computed once (row and column minima from the same popcounts): N*N*8 POPC32 per pair,
-                # against the nominal XU-pipe rate of 16 POPC/clk/SM (the kernel executes 6 per distance: two carry-save adders)
-                st["gpopc_per_s"] = round(nkp * nkp * 8 * B * cnt / (tms * 1e-3) / 1e9, 1)
-                st["frac_of_popc_peak"] = round(st["gpopc_per_s"] * 1e9 / (148 * 16 * 1.965e9), 4)
+                # every distance is computed once (row and column minima from the same popcounts): n_prev*n_cur*8 POPC32 per pair
+                # against the measured POPC rate (the kernel executes 6 per distance: two carry-save adders replace two)
+                pc = float(np.sum(n_prev * n_cur)) * 8
+                st["gpopc_per_s"] = round(pc / (tms * 1e-3) / 1e9, 1)
+                st["popc_peak_measured_g"] = round(pipe["popc_per_s"] / 1e9, 1)
+                st["frac_of_popc_peak"] = round(pc / (tms * 1e-3) / max(pipe["popc_per_s"], 1.0), 4)
+            if name == "k_ransac":
+                st["algorithmic_gflop"] = round(ransac_flop / 1e9, 3)
+                st["fp64_tflops"] = round(ransac_flop / (tms * 1e-3) / 1e12, 3)
+                st["fp64_mul_add_peak_tflops_measured"] = round(pipe["fp64_mul_add_flops"] / 1e12, 2)
+                st["frac_of_fp64_peak"] = round(ransac_flop / (tms * 1e-3) / max(pipe["fp64_mul_add_flops"], 1.0), 4)
+                st["iterations_needed"] = int(np.sum(it))
+                st["iterations_speculated"] = int(spec_iters)
+                st["iterations_wasted_frac"] = round(1.0 - float(np.sum(it)) / max(spec_iters, 1.0), 4)
+            if name == "k_cheirality":
+                st["algorithmic_gflop"] = round(cheir_flop / 1e9, 3)
+                st["fp64_tflops"] = round(cheir_flop / (tms * 1e-3) / 1e12, 3)
+                st["frac_of_fp64_peak"] = round(cheir_flop / (tms * 1e-3) / max(pipe["fp64_mul_add_flops"], 1.0), 4)
+            if name == "k_select":
+                # two retainBest passes over ~1 survivor per 130 px (3 comparisons per element for nth_element + partition) and the
+                # Harris response of 2 x quota survivors per level (7x7 block of Sobel products: ~1200 integer ops each)
+                cand = total_px / 130.0
+                iops = (3.0 * cand + 3.0 * 2 * nkp + 2 * nkp * 1200.0) * B * cnt
+                st["algorithmic_gop"] = round(iops / 1e9, 3)
+                st["frac_of_fp32_pipe_peak"] = round(iops / (tms * 1e-3) / max(pipe["fp32_mul_add_flops"] / 2.0, 1.0), 4)
             stages[name] = st
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         dms, dcnt = prof[dom]
@@ -469,13 +629,17 @@ def run_b200(a):
             achieved = alg * dcnt / (dms * 1e-3) / 1e9
         # DRAM traffic per frame of the streaming kernels from the committed `ncu --set full` capture (profiles/, 1280x1024,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch / frames per launch); null for other sizes / kernels
-        ncu_traffic_per_frame = {"k_fast_nms": (218e6 + 181e6) / 50, "k_blur": (222e6 + 178e6) / 50} \
-            if (a.width, a.height) == (1280, 1024) else {}
+        ncu_traffic_per_frame = {}
+        try:        # written from the committed ncu --set full capture by tools/ncu_summary.py
+            ncu_traffic_per_frame = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_per_frame.json"))).get("%dx%d" % (a.width, a.height), {})
+        except Exception:
+            pass
         traffic = int(ncu_traffic_per_frame[dom] * B) if dom in ncu_traffic_per_frame else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 6), "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": round(dms / tot_ms, 4), "algorithmic_bytes_per_launch": int(alg),
-                    "avg_launch_ms": round(dms / max(dcnt, 1), 4)}
+                    "avg_launch_ms": round(dms / max(dcnt, 1), 4),
+                    "measured_pipe_peaks": {k: round(v / 1e12, 3) for k, v in pipe.items()}, "measured_pipe_peaks_unit": "T op/s"}
 
     # ---- CPU baseline beside it (rank 0, bounded sample of the same workload)
     cpu = None
@@ -496,19 +660,47 @@ def run_b200(a):
         ref.close()
         cpu = {"value": done / dt, "unit": UNIT, "cores": ref.workers, "kind": ref.kind, "cpu": cpu_model(),
                "sample": "%d frame pairs of the same sequence in %.1f s: cv2 chain, both frames' ORB recomputed per pair as the reference does, one worker process per core (cv2 threads=1 each)" % (done, dt)}
+        if ref.kind == "reference":
+            # BASELINE.md section 3 figure (i), reference-faithful: ONE process, cv2's default thread count, pairs in sequence
+            import cv2
+            from oracle import cv2_chain
+            cv2.setNumThreads(-1)
+            cv2_chain.frame_pair(fr[0], fr[1], Kmat, a.nfeatures)
+            t0, n1 = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 5.0 and n1 + 1 < len(fr):
+                cv2_chain.frame_pair(fr[n1], fr[n1 + 1], Kmat, a.nfeatures)
+                n1 += 1
+            cpu["single_process"] = {"value": n1 / (time.perf_counter() - t0), "unit": UNIT, "cv2_threads": int(cv2.getNumThreads()),
+                                     "sample": "%d pairs in sequence in one process, cv2 default threading (as the reference runs)" % n1}
+
+    frames_numel = frames.numel()
+    other = None
+    if rank == 0 and world == 1 and not a.no_other_configs and a.ingest == "none":
+        del frames
+        torch.cuda.empty_cache()
+        other = other_configs(dev, with_cpu=not a.no_cpu_baseline)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
                "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
                "data": "synthetic",
-               "config": {"workload": workload_name(a), "pairs_per_step": B, "matcher_engine": a.matcher_engine, "numa_bound_cpus": numa, "frames_resident_MB": round(frames.numel() / 1e6, 1),
+               "config": {"workload": workload_name(a), "pairs_per_step": B, "matcher_engine": a.matcher_engine, "numa_bound_cpus": numa, "frames_resident_MB": round(frames_numel / 1e6, 1),
+                          "timing": "median of %d back-to-back regions of %d steps, each bracketed by barrier + synchronize, CUDA events, max over ranks" % (R_regions, K_steps),
+                          "region_ms": [round(v, 3) for v in region_ms], "allgather_ms": [round(v, 3) for v in gather_ms],
                           "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
-                              B, B * a.width * a.height / 1e6, frames.numel() / 1e6),
+                              B, B * a.width * a.height / 1e6, frames_numel / 1e6),
                           "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
                           "pairs_ok_fraction": ok_frac, "pair_stats": pair_stats},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height * (3 if a.ingest == "bgr" else 1),
-                       "d2h_bytes_per_step": B * rec, "steps": E_steps},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu}
+                       "d2h_bytes_per_step": B * rec, "steps": E_steps,
+                       "h2d_ceiling": {"GBps_per_rank": round(h2d_gbs_per_rank, 2), "GBps_all_ranks": round(world * h2d_gbs_per_rank, 2),
+                                       "pairs_per_s": round(h2d_pairs_ceiling, 1),
+                                       "how": "pinned host -> device copy of the same %d MB of frames, 3 times, all %d rank(s) at once, nothing else running" % (
+                                           e2e_frames.numel() // 1000000, world)},
+                       "frac_of_h2d_ceiling": round(e2e_value / h2d_pairs_ceiling, 4),
+                       "frac_of_resident": round(e2e_value / value, 4)},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+               "other_configs": other}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

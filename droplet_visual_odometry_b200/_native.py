@@ -48,6 +48,20 @@ def triangulate_points(P0, P1, pts0, pts1):
     return X
 
 
+PEAK_NAMES = ("fp32_fma_flops", "fp32_mul_add_flops", "fp64_fma_flops", "fp64_mul_add_flops", "popc_per_s", "int8_tensor_ops")
+
+
+def measure_peaks(device=0):
+    """Pipe rates of `device` from libdvo's microbenchmarks (dvo_measure_peaks): dict name -> ops per second."""
+    _torch()
+    lib = load_library()
+    out = np.zeros(len(PEAK_NAMES), dtype=np.float64)
+    rc = lib.dvo_measure_peaks(int(device), out.ctypes.data, len(out))
+    if rc != 0:
+        raise DvoError("dvo_measure_peaks failed (%d)" % rc)
+    return dict(zip(PEAK_NAMES, (float(v) for v in out)))
+
+
 class dvo_config(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int),
                 ("fast_threshold", ctypes.c_int), ("max_frames", ctypes.c_int), ("matcher", ctypes.c_int),
@@ -106,6 +120,7 @@ def load_library():
     lib.dvo_get_match_count.argtypes = [vp, ci, ctypes.POINTER(ci), vp]
     lib.dvo_get_frame_flags.argtypes = [vp, ci, ci, vp, vp]
     lib.dvo_triangulate_points_host.argtypes = [vp, vp, vp, vp, ci, vp]
+    lib.dvo_measure_peaks.argtypes = [ci, vp, ci]
     lib.dvo_set_features.argtypes = [vp, ci, vp, vp, ci, ci, vp]
     lib.dvo_pose_points.argtypes = [vp, ci, vp, vp, ci, vp, ci, vp]
     lib.dvo_get_poses.argtypes = [vp, ci, ci, vp, ci, vp]

@@ -375,6 +375,61 @@ k_nn_tensor(OrbBuffers ob, PairGeom pg, PairBuffers pb, int slotA0, int pair0, i
     if (warp == kEpiWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
 }
 
+// ---- int8 tensor-pipe rate (bench.py roofline denominator): every SM issues `iters` M128 x N256 x K32 MMAs back to back from
+// one resident pair of operand slabs into two alternating TMEM accumulators; no loads, no epilogue.
+__global__ void __launch_bounds__(128, 1) k_int8_mma_rate(int iters) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + kABytes, sBar = sB + kBBytes, sTmem = sBar + 16;
+    for (int i = threadIdx.x; i < (kABytes + kBBytes) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smemRaw + (base - smem_u32(smemRaw)))[i] = 0x01FF01FFu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmemBase;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(sTmem));
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < iters; ++i)
+            mma_i8(tmemBase + (i & 1) * kTileN, smem_desc(sA + (i & 7) * 2 * kLbo), smem_desc(sB + (i & 7) * 2 * kLbo), i > 1);
+        mma_commit(sBar);
+        mbar_wait(sBar, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
+}
+
+double nn_tensor_peak_tops(int numSms, int iters) {
+    const int smem = kABytes + kBBytes + 1024 + 64;
+    if (cudaFuncSetAttribute(k_int8_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_int8_mma_rate<<<numSms, 128, smem>>>(iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = 0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = 2.0 * kTileM * kTileN * 32 * (double)iters * numSms;
+        if (rep > 0 && ms > 0) best = best > ops / (ms * 1e-3) ? best : ops / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
+}
+
 int nn_tensor_rows(int maxkp) { return ((maxkp + kTileN - 1) / kTileN) * kTileN; }
 
 cudaError_t nn_tensor_init() {

@@ -204,6 +204,19 @@ void dvo_profile_enable(int on);
 int dvo_profile_collect(double* ms, int* count, int n);
 const char* dvo_profile_name(int id);
 
+/* Pipe-rate microbenchmarks for the roofline denominators that MEASURED_PEAKS.json does not carry: register-only
+ * loops on `device`, best of a few launches, CUDA events.  out[DVO_PEAK_*] in flop/s (a multiply-add counts 2, fused or not),
+ * POPC32/s, int8 op/s (tcgen05.mma.kind::i8, M128 N256 K32 issued back to back from resident shared-memory tiles).
+ * Synchronises the device; takes ~50 ms. */
+#define DVO_PEAK_FP32_FMA 0
+#define DVO_PEAK_FP32_MUL_ADD 1   /* FMUL + FADD, no contraction: what the bit-exact float32 stages execute   */
+#define DVO_PEAK_FP64_FMA 2
+#define DVO_PEAK_FP64_MUL_ADD 3   /* DMUL + DADD, no contraction: what k_ransac / k_cheirality execute        */
+#define DVO_PEAK_POPC 4
+#define DVO_PEAK_INT8_TENSOR 5
+#define DVO_PEAK_COUNT 6
+int dvo_measure_peaks(int device, double* out, int n);
+
 /* Stage taps for the parity tests (device destination, tightly packed rows of `w` bytes unless noted). */
 int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota);
 int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which /*0 pyramid, 1 blurred, 2 nms score map*/,

@@ -212,19 +212,27 @@ def test_controlled_sequence_against_the_cv2_chain_with_marker_scale():
     rng = np.random.default_rng(5)
     corners = [synth.marker_corners(p, W, H, marker) + rng.normal(scale=0.2, size=(4, 2)) for p in poses]
     vo = _vo(K, marker)
-    P_prev = K @ np.hstack((np.eye(3), np.zeros((3, 1))))
     pose = np.eye(4)
+    other_winner = 0
     for i in range(12):
         pose, rel = vo.visual_odometry_calculations(fh[i], fh[i + 1], pose, corners[i], corners[i + 1])
         ref = cv2_chain.frame_pair(fh[i], fh[i + 1], K, 500)
         assert np.array_equal(vo.last_pair["matches"], ref["matches"])
-        T, P_ref, d = cv2_chain.marker_scaled_transform(ref["R"], ref["t"], K, P_prev, corners[i], corners[i + 1], marker)
-        # the product carries ITS projection matrix forward; compare each pair's transform given the same previous one
+        # (a) the host tail on the PRODUCT's own (R, t): must equal the cv2 restatement of :309-345 to rounding, every pair
+        mine = vo.last_pair
+        Tm, _, _ = cv2_chain.marker_scaled_transform(mine["R"], mine["t"], K, vo.projection_matrix_list[-1], corners[i], corners[i + 1], marker)
+        assert np.allclose(rel, Tm, rtol=1e-9, atol=1e-9), i
+        # (b) against cv2's (R, t), given the same previous projection matrix (the product carries its own forward): inside the
+        # north-star tolerance whenever both RANSAC loops ended on the same model (see tests/test_full_sequence.py for the rest)
+        E = mine["E"]
+        if min(np.abs(E - ref["E"]).max(), np.abs(E + ref["E"]).max()) >= 1e-4:
+            other_winner += 1
+            continue
         T2, _, _ = cv2_chain.marker_scaled_transform(ref["R"], ref["t"], K, vo.projection_matrix_list[-1], corners[i], corners[i + 1], marker)
-        P_prev = P_ref
         re, de = rot_err_deg(rel[:3, :3], T2[:3, :3]), dir_err_deg(rel[:3, 3], T2[:3, 3])
         ln = np.linalg.norm(rel[:3, 3]) / np.linalg.norm(T2[:3, 3])
         assert re <= 0.1 and de <= 0.5 and abs(ln - 1.0) <= 0.02, (i, re, de, ln)
+    assert other_winner <= 2, "%d of 12 pairs ended on a different RANSAC model than cv2" % other_winner
 
 
 @pytest.mark.gpu
