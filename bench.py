@@ -415,7 +415,10 @@ def run_b200(a):
 
     B, K_steps, W_steps = a.batch, max(a.steps, 1), max(a.warmup, 3)      # timing rule: at least 3 untimed warm-up steps
     n_frames = (K_steps + W_steps) * B + 1
-    frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * 5000)
+    # ONE synthetic sequence of world * (n_frames - 1) + 1 frames, sharded by frame pair: rank r owns the contiguous block of pairs
+    # [r * P, (r + 1) * P), P = n_frames - 1, i.e. frames r * P .. (r + 1) * P -- its last frame is the next rank's first (one-frame
+    # halo, recomputed on both, as sequence.shard_pairs / run_sharded do for a trajectory extraction)
+    frames, _, Kmat = synth.render_sequence(n_frames, a.width, a.height, device=dev, start_index=rank * (n_frames - 1))
     ctx = _native.Context(a.width, a.height, nfeatures=a.nfeatures, max_frames=B + 1, device=local,
                           nn_engine=0 if a.matcher_engine == "tensor" else 1)
     Kpose = Kmat
@@ -484,6 +487,15 @@ def run_b200(a):
     ms = float(np.median(region_ms))
     value = world * npairs / (ms / 1e3)
     host_poses = poses_dev[W_steps * B * rec:(W_steps + K_steps) * B * rec].cpu().numpy().view(POSE_DTYPE)
+    chain_ms, chain_end = None, None
+    if rank == 0:      # what the all-gather is for: chain every rank's (R, t) records into one trajectory (visual_odometry_v3.py:367)
+        from droplet_visual_odometry_b200 import sequence as S
+        allrec = gathered.cpu().numpy().view(POSE_DTYPE) if world > 1 else host_poses
+        t0 = time.perf_counter()
+        traj = S.chain(S.poses_to_relatives(allrec))
+        chain_ms = (time.perf_counter() - t0) * 1e3
+        chain_end = [round(float(v), 4) for v in traj[-1][:3, 3]]
+        assert len(traj) == world * K_steps * B + 1
     ok_frac = float(np.mean(host_poses["status"] == 0))
     pair_stats = {"ransac_iters_median": float(np.median(host_poses["ransac_iters"])), "ransac_iters_max": int(host_poses["ransac_iters"].max()),
                   "matches_median": float(np.median(host_poses["n_matches"])),
@@ -689,7 +701,9 @@ def run_b200(a):
                           "region_ms": [round(v, 3) for v in region_ms], "allgather_ms": [round(v, 3) for v in gather_ms],
                           "l2_policy": "inputs larger than L2: every step reads %d new frames (%.0f MB) from a %.0f MB HBM-resident sequence" % (
                               B, B * a.width * a.height / 1e6, frames_numel / 1e6),
-                          "parallelism": "frame pairs sharded by rank, one all-gather of per-pair (R,t) records" if world > 1 else "single GPU",
+                          "parallelism": ("one sequence sharded by frame pair: contiguous blocks per rank with a one-frame halo, no data-path collective, "
+                                          "one NCCL all-gather of the per-pair (R,t) records per region, then the 4x4 chain on rank 0") if world > 1 else "single GPU",
+                          "chain": {"host_ms": None if chain_ms is None else round(chain_ms, 2), "pairs": world * K_steps * B, "end_position": chain_end},
                           "pairs_ok_fraction": ok_frac, "pair_stats": pair_stats},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * a.width * a.height * (3 if a.ingest == "bgr" else 1),
                        "d2h_bytes_per_step": B * rec, "steps": E_steps,

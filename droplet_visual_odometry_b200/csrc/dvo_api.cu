@@ -89,8 +89,9 @@ static int alloc_orb_buffers(dvo_ctx* ctx, OrbBuffers& b) {
 #define DA(p, n) if ((rc = dalloc(ctx, &(p), (n))) != 0) return rc
     DA(b.pyr, S * g.slotStride + 4096);
     DA(b.blur, S * g.slotStride + 4096);
-    DA(b.map, S * g.slotStride + 4096);
-    DA(b.rowCount, S * g.rowsPerSlot);
+    DA(b.tileCnt, S * g.tilesPerFrame * kTileH);
+    DA(b.tileTot, S * g.tilesPerFrame);
+    DA(b.tileList, S * (size_t)g.tilesPerFrame * kTileListCap);
     DA(b.cand, S * g.candPerSlot);
     DA(b.candCount, S * kMaxLevels);
     DA(b.pairs, S * g.candPerSlot);
@@ -627,10 +628,10 @@ int dvo_get_frame_flags(dvo_ctx* ctx, int slot0, int n, int32_t* h_flags, void* 
 }
 
 int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which, uint8_t* d_dst, void* stream) {
-    if (!ctx || !d_dst || slot < 0 || slot >= ctx->nSlots || level < 0 || level >= ctx->og.nlevels || which < 0 || which > 2)
+    if (!ctx || !d_dst || slot < 0 || slot >= ctx->nSlots || level < 0 || level >= ctx->og.nlevels || which < 0 || which > 1)
         return DVO_E_INVALID;
     const LevelGeom& lv = ctx->og.lv[level];
-    const uint8_t* base = which == 0 ? ctx->ob.pyr : (which == 1 ? ctx->ob.blur : ctx->ob.map);
+    const uint8_t* base = which == 0 ? ctx->ob.pyr : ctx->ob.blur;
     CK(cudaMemcpy2DAsync(d_dst, lv.w, base + (size_t)slot * ctx->og.slotStride + lv.off, lv.pitch, lv.w, lv.h,
                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DVO_OK;
@@ -945,7 +946,7 @@ int dvo_profile_collect(double* ms, int* count, int n) {
     return PF_COUNT;
 }
 const char* dvo_profile_name(int id) {
-    static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_compact", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
+    static const char* names[PF_COUNT] = {"k_pyr_down", "k_fast_nms", "k_gather", "k_select", "k_angle_pack", "k_blur", "k_brief", "k_nn",
                                           "k_match_sort", "k_ransac", "k_cheirality", "k_pose_final", "k_load_or_ingest"};
     return (id >= 0 && id < PF_COUNT) ? names[id] : "";
 }

@@ -1,8 +1,8 @@
 // Internal layout of a dvo context: HBM buffers, per-level geometry, kernel launch entry points.
 //
 // HBM layout (DESIGN.md "Data layout"): everything is per frame SLOT (one slot per frame in flight).
-//   pyr / blur / map : u8 images, 8 levels each, row pitch = roundup(w, 128), levels 256-B aligned, slot stride fixed
-//   rowCount         : int32 per pyramid row (survivor count after NMS), zeroed per batch
+//   pyr / blur       : u8 images, 8 levels each, row pitch = roundup(w, 128), levels 256-B aligned, slot stride fixed
+//   tileList/Cnt/Tot : NMS survivors of every 128x32 FAST tile, in (row, x) order, with per-(tile,row) and per-tile counts
 //   cand             : u32 per candidate, packed score<<24 | y<<12 | x, raster order per level
 //   pairs            : u64 per first-cut survivor, harris f32 bits <<32 | packed xy, cv2 order
 //   fin*             : final keypoints per level in cv2 order
@@ -23,6 +23,7 @@ constexpr int kTileH = 32;
 constexpr int kFastHaloL = 16;       // TMA needs the inner start coordinate 16-byte aligned: left halo is 16 px (4 used)
 constexpr int kFastBoxW = 160;       // TMA box: 16 + tile + 16 (multiple of 16 bytes)
 constexpr int kFastBoxH = 40;
+constexpr int kTileListCap = (kTileW / 2) * (kTileH / 2);   // strict 3x3 NMS: no two survivors touch
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
 constexpr int kSelectSmallSmemBytes = 64 * 1024;     // k_select launch for the small pyramid levels (3 CTAs per SM)
@@ -54,8 +55,9 @@ struct OrbGeom {
 struct OrbBuffers {
     uint8_t* pyr;
     uint8_t* blur;
-    uint8_t* map;
-    int* rowCount;           // [slots][rowsPerSlot]
+    uint16_t* tileCnt;       // [slots][tilesPerFrame][kTileH]  NMS survivors per (tile, row)
+    int* tileTot;            // [slots][tilesPerFrame]          ... per tile
+    uint32_t* tileList;      // [slots][tilesPerFrame][kTileListCap] survivors of a tile in (row, x) order, packed like cand
     uint32_t* cand;          // [slots][candPerSlot]
     int* candCount;          // [slots][8]
     unsigned long long* pairs;   // [slots][candPerSlot]

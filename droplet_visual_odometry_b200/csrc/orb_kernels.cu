@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     constexpr int kList2Cap = (kTileH + 2) * (kTileW + 2);
     __shared__ uint16_t list2[kList2Cap];
     __shared__ int s_n1, s_n2;
-    __shared__ int s_rowcnt[kTileH];
+    __shared__ int s_rowcnt[kTileH + 8];
     __shared__ __align__(8) unsigned long long bar;
 
     const uint32_t ti = __ldg(b.tileInfo + blockIdx.x);
@@ -353,23 +353,63 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     }
     __syncthreads();
 
-    // ---- phase 5: score map tile -> HBM (one 16-byte store per thread), per-row survivor counts
+    // ---- phase 5: the tile's survivors go straight from the shared output tile to this tile's list, in (row, x) order: a
+    // thread owns 16 consecutive pixels of a row, so thread order is raster order and one CTA-wide scan places every entry.
+    // (The full-resolution score map this kernel used to store -- and k_compact to re-read -- was 2/3 of its DRAM traffic.)
     {
-        uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
+        const int warp = tid >> 5;
         const int r = tid >> 3, c16 = (tid & 7) * 16;
-        const int y = y0 + r;
-        if (y < lv.h) *reinterpret_cast<uint4*>(map + (size_t)y * lv.pitch + x0 + c16) = reinterpret_cast<const uint4*>(outmap)[tid];
-        if (tid < kTileH && y0 + tid < lv.h) {
-            const int c = s_rowcnt[tid];
-            if (c > 0) atomicAdd(b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase + y0 + tid, c);
+        const uint4 v = reinterpret_cast<const uint4*>(outmap)[tid];
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t nzw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)      // bytes != 0 -> their top bit
+            nzw[q] = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
+        const int c = __popc((nzw[0] >> 7) | (nzw[1] >> 6) | (nzw[2] >> 5) | (nzw[3] >> 4));
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
         }
+        int* s_wsum = s_rowcnt + kTileH;      // 8 warp totals behind the 32 row counts
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int t = s_wsum[w];
+            base += w < warp ? t : 0;
+            total += t;
+        }
+        const size_t tileIdx = (size_t)slot * g.tilesPerFrame + blockIdx.x;
+        if (c) {      // at most 8 survivors in 16 pixels (no two are adjacent)
+            uint32_t* list = b.tileList + tileIdx * kTileListCap + (base + incl - c);
+            const uint32_t yx = ((uint32_t)(y0 + r) << 12) | (uint32_t)(x0 + c16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t m = nzw[q];
+                while (m) {
+                    const int k = (__ffs(m) - 1) >> 3;
+                    *list++ = (((wv[q] >> (8 * k)) & 0xFFu) << 24) | (yx + (uint32_t)(4 * q + k));
+                    m &= m - 1;
+                }
+            }
+        }
+        if (tid < kTileH) b.tileCnt[tileIdx * kTileH + tid] = (uint16_t)s_rowcnt[tid];
+        if (tid == 0) b.tileTot[tileIdx] = total;
     }
 }
 
-// =========================================================================================== compaction
-__global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int slot0) {
+// =========================================================================================== raster-order gather
+// The per-tile survivor lists of one 32-row band of a level -> the level's raster-order candidate list (cv2's FAST output
+// order, which retainBest's order-exact replay depends on).  Only survivors move: ~8 bytes each.
+__global__ void __launch_bounds__(256) k_gather(OrbGeom g, OrbBuffers b, int slot0) {
     __shared__ int s_red[8];
     __shared__ int s_rowOff[33];
+    __shared__ uint16_t s_cnt[32][33];      // [tile in band][row]; a level is at most 4096 / 128 = 32 tiles wide
+    __shared__ uint16_t s_src[32][33];      // offset of (tile, row) inside the tile's list
+    __shared__ uint16_t s_dst[32][33];      // offset of (tile, row) inside the row's run of the level list
     const int rb = blockIdx.x;
     int L = 0;
 #pragma unroll
@@ -377,73 +417,46 @@ __global__ void __launch_bounds__(256) k_compact(OrbGeom g, OrbBuffers b, int sl
         if (i < g.nlevels && rb >= g.lv[i].rbBase) L = i;
     const LevelGeom lv = g.lv[L];
     const int slot = slot0 + blockIdx.y;
-    const int row0 = (rb - lv.rbBase) * 32;
-    const int* rowCount = b.rowCount + (size_t)slot * g.rowsPerSlot + lv.rowBase;
+    const int band = rb - lv.rbBase, tilesX = lv.tilesX;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // base = sum of counts of rows [0, row0)
+    const size_t tile0 = (size_t)slot * g.tilesPerFrame + lv.tileBase;
+    // base = survivors of every band above this one
     int acc = 0;
-    for (int r = tid; r < row0; r += 256) acc += rowCount[r];
+    for (int i = tid; i < band * tilesX; i += 256) acc += b.tileTot[tile0 + i];
     acc = __reduce_add_sync(0xffffffffu, acc);
     if (lane == 0) s_red[warp] = acc;
+    const uint16_t* cnt = b.tileCnt + (tile0 + (size_t)band * tilesX) * kTileH;
+    for (int i = tid; i < tilesX * kTileH; i += 256) s_cnt[i >> 5][i & 31] = cnt[i];
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0) {          // lane = row: run of the row in the level list
+        int c = 0;
+        for (int t = 0; t < tilesX; ++t) { s_dst[t][lane] = (uint16_t)c; c += s_cnt[t][lane]; }
         int base = 0;
         for (int i = 0; i < 8; ++i) base += s_red[i];
-        int r = row0 + lane;
-        int c = (r < lv.h) ? rowCount[r] : 0;
-        // exclusive scan over the 32 rows
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, incl, o);
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += n;
         }
         s_rowOff[lane] = base + incl - c;
         if (lane == 31) s_rowOff[32] = base + incl;
+    } else if (warp == 1 && lane < tilesX) {      // lane = tile: start of each row inside the tile's list
+        int c = 0;
+        for (int r = 0; r < kTileH; ++r) { s_src[lane][r] = (uint16_t)c; c += s_cnt[lane][r]; }
     }
     __syncthreads();
-    if (row0 + 32 >= lv.h && tid == 0) b.candCount[slot * kMaxLevels + L] = s_rowOff[32];
-
-    const uint8_t* map = b.map + (size_t)slot * g.slotStride + lv.off;
+    if (band == lv.tilesY - 1 && tid == 0) b.candCount[slot * kMaxLevels + L] = s_rowOff[32];
     uint32_t* cand = b.cand + (size_t)slot * g.candPerSlot + lv.candBase;
-    for (int rr = warp; rr < 32; rr += 8) {
-        int y = row0 + rr;
-        if (y >= lv.h) break;
-        int n = s_rowOff[rr + 1] - s_rowOff[rr];
+    const uint32_t* lists = b.tileList + (tile0 + (size_t)band * tilesX) * kTileListCap;
+    for (int i = tid; i < kTileH * tilesX; i += 256) {      // row-major over (row, tile): neighbouring threads write neighbouring runs
+        const int r = i / tilesX, t = i - r * tilesX;
+        const int n = s_cnt[t][r];
         if (n == 0) continue;
-        int running = s_rowOff[rr];
-        for (int xc = 0; xc < lv.w; xc += 512) {      // 16 pixels per lane per step
-            const int x = xc + lane * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (x < lv.pitch) v = *reinterpret_cast<const uint4*>(map + (size_t)y * lv.pitch + x);
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nzw[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)      // bytes != 0 -> their top bit
-                nzw[q] = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
-            const int c = __popc((nzw[0] >> 7) | (nzw[1] >> 6) | (nzw[2] >> 5) | (nzw[3] >> 4));      // one POPC for 16 bytes
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int nn = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += nn;
-            }
-            int pos = running + incl - c;
-            if (c) {      // survivors are sparse (a few per 16 pixels at most): walk the set bits only
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t m = nzw[q];
-                    while (m) {
-                        const int k = (__ffs(m) - 1) >> 3;
-                        const uint32_t sv = (wv[q] >> (8 * k)) & 0xFFu;
-                        if (pos < lv.candCap) cand[pos] = (sv << 24) | ((uint32_t)y << 12) | (uint32_t)(x + 4 * q + k);
-                        ++pos;
-                        m &= m - 1;
-                    }
-                }
-            }
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
+        const uint32_t* src = lists + (size_t)t * kTileListCap + s_src[t][r];
+        int dst = s_rowOff[r] + s_dst[t][r];
+        for (int k = 0; k < n; ++k, ++dst)
+            if (dst < lv.candCap) cand[dst] = src[k];
     }
 }
 
@@ -1191,7 +1204,6 @@ void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& i
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st, const SideStreams* ss) {
     if (nSlots <= 0) return;
-    cudaMemsetAsync(b.rowCount + (size_t)slot0 * g.rowsPerSlot, 0, sizeof(int) * (size_t)nSlots * g.rowsPerSlot, st);
     for (int L = 1; L < g.nlevels; ++L) {
         const long long ctas8 = (long long)((g.lv[L].w + 127) / 128) * ((g.lv[L].h + 63) / 64) * nSlots;
         const int rows = ctas8 >= 148 * 16 ? 8 : 2;
@@ -1218,9 +1230,9 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
         ++g_launches;
         cudaEventRecord(ss->evJoin, ss->side);
     }
-    { ProfScope ps_(PF_COMPACT, st); k_compact<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
+    { ProfScope ps_(PF_COMPACT, st); k_gather<<<dim3(g.rowBlocksPerFrame, nSlots), 256, 0, st>>>(g, b, slot0); }
     ++g_launches;
-    debug_sync("k_compact", st);
+    debug_sync("k_gather", st);
     {
         // Large levels: 1024 threads and the whole 160 KB working array (one CTA per SM).  Small levels (candidate lists
         // that fit 64 KB): 512 threads, three CTAs per SM, on a second side stream so both groups run together.

@@ -219,7 +219,7 @@ int dvo_measure_peaks(int device, double* out, int n);
 
 /* Stage taps for the parity tests (device destination, tightly packed rows of `w` bytes unless noted). */
 int dvo_level_size(const dvo_ctx* ctx, int level, int* w, int* h, int* quota);
-int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which /*0 pyramid, 1 blurred, 2 nms score map*/,
+int dvo_tap_image(dvo_ctx* ctx, int slot, int level, int which /*0 pyramid, 1 blurred*/,
                   uint8_t* d_dst, void* stream);
 int dvo_tap_candidates(dvo_ctx* ctx, int slot, int level, uint32_t* d_dst /*packed score<<24|y<<12|x*/, int capacity,
                        int* h_count /*host, synchronises*/, void* stream);
