@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     constexpr int kList2Cap = (kTileH + 2) * (kTileW + 2);
     __shared__ uint16_t list2[kList2Cap];
     __shared__ int s_n1, s_n2;
-    __shared__ int s_rowcnt[kTileH + 8];
+    __shared__ int s_rowcnt[2 * kTileH];
     __shared__ __align__(8) unsigned long long bar;
 
     const uint32_t ti = __ldg(b.tileInfo + blockIdx.x);
@@ -313,10 +313,12 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     }
     __syncthreads();
 
-    // ---- phase 3: scores of the corners into the ring score tile; list1 is dead now and becomes the output tile
-    uint8_t* outmap = reinterpret_cast<uint8_t*>(list1);        // [kTileH][kTileW], zero = no keypoint
-    reinterpret_cast<uint4*>(outmap)[tid] = make_uint4(0, 0, 0, 0);
+    // ---- phase 3: scores of the corners into the ring score tile; list1 is dead now and becomes the survivor staging area
+    uint32_t* stage = reinterpret_cast<uint32_t*>(list1);                    // [kTileListCap] packed survivors, any order
+    uint16_t* stageIdx = reinterpret_cast<uint16_t*>(stage + kTileListCap);  // [kTileListCap] arrival index within the row
+    static_assert(sizeof(list1) >= kTileListCap * 6, "survivor staging does not fit the dead prefilter list");
     if (tid < kTileH) s_rowcnt[tid] = 0;
+    if (tid == 0) s_n1 = 0;                                                  // reused as the survivor counter
     const int n2 = s_n2;
     for (int i = tid; i < n2; i += 256) {
         const int e = list2[i];
@@ -330,7 +332,8 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
     }
     __syncthreads();
 
-    // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull
+    // ---- phase 4: strict 3x3 NMS, driven by the corner list (non-corners score 0), 31-px border cull.  A survivor takes the
+    // next place of its row (shared atomic) and is parked in the staging list.
     const int border = 31;
     for (int i = tid; i < n2; i += 256) {
         const int code = list2[i] & 0x1FFF;
@@ -345,59 +348,40 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         const uint8_t* q = sc + cy * 136 + cx;
         const int sv = *q;
         const int nmax = imax3(imax3(q[-136 - 1], q[-136], q[-136 + 1]), imax3(q[-1], q[1], q[136 - 1]), imax(q[136], q[136 + 1]));
-        const bool keep = sv > nmax;
-        if (keep) {
-            outmap[(cy - 1) * kTileW + (cx - 1)] = (uint8_t)sv;
-            smem_red_add(&s_rowcnt[cy - 1], 1);
+        if (sv > nmax) {
+            const int k = smem_atom_add(&s_rowcnt[cy - 1], 1);
+            const int p = smem_atom_add(&s_n1, 1);
+            stage[p] = ((uint32_t)sv << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+            stageIdx[p] = (uint16_t)k;
         }
     }
     __syncthreads();
 
-    // ---- phase 5: the tile's survivors go straight from the shared output tile to this tile's list, in (row, x) order: a
-    // thread owns 16 consecutive pixels of a row, so thread order is raster order and one CTA-wide scan places every entry.
-    // (The full-resolution score map this kernel used to store -- and k_compact to re-read -- was 2/3 of its DRAM traffic.)
+    // ---- phase 5: the tile's survivors -> this tile's list in HBM, grouped by row (k_gather orders the few entries of a
+    // (tile, row) run by x).  Nothing else is written: the full-resolution score map this kernel used to store -- and k_compact
+    // to re-read -- was 2/3 of its DRAM traffic.
     {
-        const int warp = tid >> 5;
-        const int r = tid >> 3, c16 = (tid & 7) * 16;
-        const uint4 v = reinterpret_cast<const uint4*>(outmap)[tid];
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        uint32_t nzw[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)      // bytes != 0 -> their top bit
-            nzw[q] = ((wv[q] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[q]) & 0x80808080u;
-        const int c = __popc((nzw[0] >> 7) | (nzw[1] >> 6) | (nzw[2] >> 5) | (nzw[3] >> 4));
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        int* s_wsum = s_rowcnt + kTileH;      // 8 warp totals behind the 32 row counts
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const int t = s_wsum[w];
-            base += w < warp ? t : 0;
-            total += t;
-        }
         const size_t tileIdx = (size_t)slot * g.tilesPerFrame + blockIdx.x;
-        if (c) {      // at most 8 survivors in 16 pixels (no two are adjacent)
-            uint32_t* list = b.tileList + tileIdx * kTileListCap + (base + incl - c);
-            const uint32_t yx = ((uint32_t)(y0 + r) << 12) | (uint32_t)(x0 + c16);
+        int* s_rowOff = s_rowcnt + kTileH;       // 32 exclusive offsets
+        if (tid < 32) {
+            const int c = s_rowcnt[tid];
+            int incl = c;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t m = nzw[q];
-                while (m) {
-                    const int k = (__ffs(m) - 1) >> 3;
-                    *list++ = (((wv[q] >> (8 * k)) & 0xFFu) << 24) | (yx + (uint32_t)(4 * q + k));
-                    m &= m - 1;
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
             }
+            s_rowOff[tid] = incl - c;
+            b.tileCnt[tileIdx * kTileH + tid] = (uint16_t)c;
+            if (tid == 31) b.tileTot[tileIdx] = incl;
         }
-        if (tid < kTileH) b.tileCnt[tileIdx * kTileH + tid] = (uint16_t)s_rowcnt[tid];
-        if (tid == 0) b.tileTot[tileIdx] = total;
+        __syncthreads();
+        const int n3 = s_n1;
+        uint32_t* list = b.tileList + tileIdx * kTileListCap;
+        for (int i = tid; i < n3; i += 256) {
+            const uint32_t e = stage[i];
+            list[s_rowOff[((e >> 12) & 0xFFFu) - y0] + stageIdx[i]] = e;
+        }
     }
 }
 
@@ -454,9 +438,17 @@ __global__ void __launch_bounds__(256) k_gather(OrbGeom g, OrbBuffers b, int slo
         const int n = s_cnt[t][r];
         if (n == 0) continue;
         const uint32_t* src = lists + (size_t)t * kTileListCap + s_src[t][r];
-        int dst = s_rowOff[r] + s_dst[t][r];
-        for (int k = 0; k < n; ++k, ++dst)
-            if (dst < lv.candCap) cand[dst] = src[k];
+        const int dst = s_rowOff[r] + s_dst[t][r];
+        if (n == 1) {
+            if (dst < lv.candCap) cand[dst] = src[0];
+            continue;
+        }
+        for (int k = 0; k < n; ++k) {        // a run arrives in atomic order: place each entry by its rank in x (runs are a few entries)
+            const uint32_t e = src[k];
+            int rank = 0;
+            for (int q = 0; q < n; ++q) rank += (src[q] & 0xFFFu) < (e & 0xFFFu) ? 1 : 0;
+            if (dst + rank < lv.candCap) cand[dst + rank] = e;
+        }
     }
 }
 
