@@ -443,6 +443,19 @@ __global__ void __launch_bounds__(256) k_gather(OrbGeom g, OrbBuffers b, int slo
             if (dst < lv.candCap) cand[dst] = src[0];
             continue;
         }
+        if (n <= 4) {        // the common case from registers: four loads, six comparisons
+            const uint32_t e0 = src[0], e1 = src[1], e2 = n > 2 ? src[2] : 0xFFFFFFFFu, e3 = n > 3 ? src[3] : 0xFFFFFFFFu;
+            const uint32_t a0 = e0 & 0xFFFu, a1 = e1 & 0xFFFu, a2 = n > 2 ? (e2 & 0xFFFu) : 0x1000u, a3 = n > 3 ? (e3 & 0xFFFu) : 0x1001u;
+            const int l01 = a0 < a1, l02 = a0 < a2, l03 = a0 < a3, l12 = a1 < a2, l13 = a1 < a3, l23 = a2 < a3;
+            const int r0 = 3 - l01 - l02 - l03, r1 = l01 + 2 - l12 - l13, r2 = l02 + l12 + 1 - l23, r3 = l03 + l13 + l23;
+            if (dst + n <= lv.candCap) {
+                cand[dst + r0] = e0;
+                cand[dst + r1] = e1;
+                if (n > 2) cand[dst + r2] = e2;
+                if (n > 3) cand[dst + r3] = e3;
+            }
+            continue;
+        }
         for (int k = 0; k < n; ++k) {        // a run arrives in atomic order: place each entry by its rank in x (runs are a few entries)
             const uint32_t e = src[k];
             int rank = 0;
