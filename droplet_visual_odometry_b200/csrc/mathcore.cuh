@@ -199,75 +199,6 @@ DVO_HD uint32_t fast_prefilter_u8x4(uint32_t c, uint32_t n, uint32_t e, uint32_t
     return (mn | ms) & (me | mw) & 0x80808080u;
 }
 
-// ---- exact FAST-9/16 test of FOUR horizontally adjacent pixels at once (one per byte) ------------------------------------
-// Byte-wise unsigned a > b, result in bit 7 of every byte (other bits are garbage): the carry out of a + ~b.  The low seven
-// bits are added without crossing bytes, the top bits are a full-adder carry = majority(a7, ~b7, carry-in).
-DVO_HD uint32_t prmt_u32(uint32_t a, uint32_t b, uint32_t sel) {
-#if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
-#else
-    uint64_t w = ((uint64_t)b << 32) | a;
-    uint32_t r = 0;
-    for (int i = 0; i < 4; ++i) r |= (uint32_t)((w >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
-    return r;
-#endif
-}
-DVO_HD uint32_t gtu8x4_top(uint32_t a, uint32_t b) {
-    const uint32_t s = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
-    return (a & ~b) | ((a | ~b) & s);
-}
-// `img` points at the first of the four centre pixels (4-byte aligned), `pitch` is the row pitch in bytes (multiple of 4).
-// Returns a word whose bit 7 of byte j says "pixel j has 9 contiguous ring pixels brighter than v + t" and bit 6 the same for
-// darker than v - t (every other bit is garbage).  The 16 ring words are built from aligned 32-bit loads + PRMT, the two
-// comparisons of a ring position cost three instructions each with the centre-derived halves hoisted, the flags of both
-// polarities share one register per ring position (brighter in bit 7, darker in bit 6), and the nine-arc test is 40 three-input
-// logic operations on those 16 registers: ~240 instructions for four pixels against ~115 for one with scalar ring reads.
-DVO_HDN uint32_t fast_quad_arcs(const uint8_t* img, int pitch, int t) {
-    const int dxs[16] = DVO_FAST_DX, dys[16] = DVO_FAST_DY;
-    const uint32_t C = *reinterpret_cast<const uint32_t*>(img);
-    const uint32_t T = 0x01010101u * (uint32_t)t;
-    // hi = min(C + t, 255), lo = max(C - t, 0) per byte
-    uint32_t hi, lo;
-    {
-        const uint32_t sum7 = (C & 0x7f7f7f7fu) + (T & 0x7f7f7f7fu);               // low 7 bits + carry into bit 7
-        const uint32_t top = (C & T) | ((C | T) & sum7);                           // carry out of bit 7 (bit 7 of each byte)
-        const uint32_t full = sum7 ^ ((C ^ T) & 0x80808080u);                      // the wrapped byte sums
-        const uint32_t ov = ((top & 0x80808080u) >> 7) * 0xFFu;                    // 0xFF in every overflowing byte
-        hi = full | ov;
-        const uint32_t lt = gtu8x4_top(T, C);                                      // t > c  -> result 0
-        const uint32_t d7 = ((C | 0x80808080u) - (T & 0x7f7f7f7fu));               // per-byte c - t with a borrow guard
-        const uint32_t diff = d7 ^ ((~(C ^ T)) & 0x80808080u);
-        lo = diff & ~(((lt & 0x80808080u) >> 7) * 0xFFu);
-    }
-    const uint32_t hiN = ~hi & 0x7f7f7f7fu, lo7 = lo & 0x7f7f7f7fu;
-    uint32_t W[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int dx = dxs[k], dy = dys[k];
-        const uint8_t* rowp = img + dy * pitch;
-        uint32_t P;
-        if (dx == 0) P = *reinterpret_cast<const uint32_t*>(rowp);
-        else if (dx > 0)
-            P = prmt_u32(*reinterpret_cast<const uint32_t*>(rowp), *reinterpret_cast<const uint32_t*>(rowp + 4),
-                         dx == 1 ? 0x4321u : (dx == 2 ? 0x5432u : 0x6543u));
-        else
-            P = prmt_u32(*reinterpret_cast<const uint32_t*>(rowp - 4), *reinterpret_cast<const uint32_t*>(rowp),
-                         dx == -1 ? 0x6543u : (dx == -2 ? 0x5432u : 0x4321u));
-        const uint32_t sb = (P & 0x7f7f7f7fu) + hiN;
-        const uint32_t B = (P & ~hi) | ((P | ~hi) & sb);            // P > hi  in bit 7
-        const uint32_t sd = lo7 + (~P & 0x7f7f7f7fu);
-        const uint32_t D = (lo & ~P) | ((lo | ~P) & sd);            // lo > P  in bit 7
-        W[k] = (B & 0x80808080u) | ((D >> 1) & ~0x80808080u);       // brighter flag in bit 7, darker flag in bit 6
-    }
-    uint32_t A3[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) A3[k] = W[k] & W[(k + 1) & 15] & W[(k + 2) & 15];
-    uint32_t R = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) R |= A3[k] & A3[(k + 3) & 15] & A3[(k + 6) & 15];
-    return R;
-}
-
 // ---- A.3 Harris ------------------------------------------------------------------------------------------------
 DVO_HD float harris_from_sums(int a, int b, int c) {
     const float scale = fdiv(1.0f, fmul(28.0f, 255.0f));

@@ -254,12 +254,10 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
                 pass = fast_prefilter_u8x4(c, up, e, dn, w, th) & colmask;
             }
             passw[sw] = pass;
-            cnt += pass != 0 ? 1 : 0;
+            cnt += __popc(pass);
         }
-        // A QUAD with at least one passing pixel becomes one list entry (a fifth of the quads of a textured frame): raw offset of
-        // its first pixel | the four pass bits << 24.  Warp-wide exclusive scan of the per-thread entry counts; each warp reserves
-        // its share of the list with one shared atomic (the order is irrelevant), then one predicated append per sweep through
-        // a running 32-bit shared address.
+        // warp-wide exclusive scan of the per-thread survivor counts; each warp reserves its share of list1 with one
+        // shared atomic (the list order is irrelevant: every later phase writes through maps), then every thread appends
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -269,65 +267,49 @@ __global__ void __launch_bounds__(256, 7) k_fast_nms(OrbGeom g, OrbBuffers b, co
         int base = 0;
         if (lane == 31 && incl > 0) base = smem_atom_add(&s_n1, incl);
         base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t la = (uint32_t)__cvta_generic_to_shared(list1) + 4u * (uint32_t)(base + incl - cnt);
+        // four predicated appends per sweep through a 32-bit shared address (no divergent walk over the set bits, and no
+        // re-derivation of the list base under every predicate)
+        uint32_t la = (uint32_t)__cvta_generic_to_shared(list1) + 2u * (uint32_t)(base + incl - cnt);
 #pragma unroll
         for (int sw = 0; sw < kSweeps; ++sw) {
             const uint32_t m = passw[sw];
-            const uint32_t code0 = (uint32_t)((sw * kRowsPerSweep + qrow + 3) * kFastBoxW + 12 + 4 * qx);
-            // bits 7, 15, 23, 31 of m -> bits 24..27 (the products of the four flags with 2^3, 2^10, 2^17, 2^24 do not collide)
-            const uint32_t entry = ((((m >> 7) & 0x01010101u) * 0x01020408u) & 0x0F000000u) | code0;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.u32 p, %2, 0;\n\t"
-                "@p st.shared.u32 [%0], %1;\n\t"
-                "@p add.u32 %0, %0, 4;\n\t}"
-                : "+r"(la)
-                : "r"(entry), "r"(m)
-                : "memory");
+            const int code0 = (sw * kRowsPerSweep + qrow + 3) * kFastBoxW + 12 + 4 * qx;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                    "and.b32 t, %2, %3;\n\t"
+                    "setp.ne.u32 p, t, 0;\n\t"
+                    "@p st.shared.u16 [%0], %1;\n\t"
+                    "@p add.u32 %0, %0, 2;\n\t}"
+                    : "+r"(la)
+                    : "h"((uint16_t)(code0 + q)), "r"(m), "r"(0x80u << (8 * q))
+                    : "memory");
         }
     }
     __syncthreads();
 
-    // ---- phase 2: exact 9-of-16 test of the listed quads, four pixels at a time in packed bytes (fast_quad_arcs); the corners
-    // (pixel offset | polarity << 13) go to list2
+    // ---- phase 2: exact 16-point corner test on the survivors
     const int dxs[16] = DVO_FAST_DX, dys[16] = DVO_FAST_DY;
     const int n1 = s_n1;
-    const uint32_t* qlist = reinterpret_cast<const uint32_t*>(list1);
     for (int i0 = 0; i0 < n1; i0 += 256) {
         const int i = i0 + tid;
-        uint32_t any = 0, R = 0, code = 0;
+        int pol = 0;
+        int code = 0;
         if (i < n1) {
-            const uint32_t entry = qlist[i];
-            code = entry & 0x1FFFu;
-            R = fast_quad_arcs(raw + code, kFastBoxW, th);
-            const uint32_t pm = (((entry >> 24) * 0x00204081u) & 0x01010101u) << 7;      // pass bit k -> bit 7 of byte k
-            any = (R | (R << 1)) & pm;
-        }
-        const int c = __popc(any);
-        int incl = c;
+            code = list1[i];
+            const uint8_t* c = raw + code;
+            int pr[16];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
+            for (int k = 0; k < 16; ++k) pr[k] = c[dys[k] * kFastBoxW + dxs[k]];
+            pol = fast_corner_polarity16(*c, pr, th);
         }
+        const bool corner = pol != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, corner);
         int base = 0;
-        if (lane == 31 && incl > 0) base = smem_atom_add(&s_n2, incl);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t la = (uint32_t)__cvta_generic_to_shared(list2) + 2u * (uint32_t)(base + incl - c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            // polarity bits of pixel q: bit 0 = ring darker than v - t (R bit 6), bit 1 = ring brighter than v + t (R bit 7)
-            const uint32_t e = (code + q) | (((R >> (8 * q + 6)) & 3u) << 13);            // code < 6400 < 2^13
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                "and.b32 t, %2, %3;\n\t"
-                "setp.ne.u32 p, t, 0;\n\t"
-                "@p st.shared.u16 [%0], %1;\n\t"
-                "@p add.u32 %0, %0, 2;\n\t}"
-                : "+r"(la)
-                : "h"((uint16_t)e), "r"(any), "r"(0x80u << (8 * q))
-                : "memory");
-        }
+        if (lane == 0 && m) base = smem_atom_add(&s_n2, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (corner) list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(code | (pol << 13));   // code < 6400 < 2^13
     }
     __syncthreads();
 

@@ -124,25 +124,6 @@ int hs_fast_prefilter_check(const uint8_t* img, int w, int h, int pitch, int t, 
     return missed;
 }
 
-// packed four-pixel exact test against the scalar one on every aligned quad of an image: returns the number of pixels whose
-// (brighter, darker) arc flags differ (must be 0)
-int hs_fast_quad_check(const uint8_t* img, int w, int h, int pitch, int t) {
-    const int dx[16] = DVO_FAST_DX, dy[16] = DVO_FAST_DY;
-    int bad = 0;
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 4; x + 4 <= w - 4; x += 4) {
-            const uint32_t R = fast_quad_arcs(img + (size_t)y * pitch + x, pitch, t);
-            for (int k = 0; k < 4; ++k) {
-                int p[16];
-                for (int j = 0; j < 16; ++j) p[j] = img[(y + dy[j]) * pitch + x + k + dx[j]];
-                const int pol = fast_corner_polarity16(img[y * pitch + x + k], p, t);
-                const int got = (int)((R >> (8 * k + 6)) & 1) | ((int)((R >> (8 * k + 7)) & 1) << 1);   // pol bit 0: ring darker than v - t, bit 1: brighter
-                if (got != pol) ++bad;
-            }
-        }
-    return bad;
-}
-
 // exhaustive check of the one-IMAD ring comparison used by the device build of fast_corner_polarity16: returns the number of
 // (v, t, p) triples, all in 0..255, where a flag differs from the plain comparison (must be 0)
 int hs_fast_ring_flags_check() {

@@ -78,22 +78,6 @@ def test_fast_packed_prefilter_never_rejects_a_corner(hostsim, golden):
             assert passed.value < img.size
 
 
-def test_fast_packed_quad_test_equals_the_scalar_test(hostsim, golden):
-    """fast_quad_arcs (four pixels per word: packed byte compares, both polarities in one flag register per ring position, the
-    nine-arc test as three-input logic) against fast_corner_polarity16 on every aligned quad -- real texture, noise, blocky
-    images, and values around the saturation edges of v +- t; thresholds from 1 to 255."""
-    rng = np.random.default_rng(6)
-    h, w = 96, 160
-    base = rng.integers(0, 256, (h // 8 + 1, w // 8 + 1))
-    blocky = (np.kron(base, np.ones((8, 8)))[:h, :w] + rng.integers(-3, 4, (h, w))).clip(0, 255).astype(np.uint8)
-    imgs = [np.ascontiguousarray(golden["frame0"][:240, :320]), rng.integers(0, 256, (h, w)).astype(np.uint8), blocky,
-            rng.choice([0, 1, 19, 20, 21, 22, 128, 234, 235, 236, 254, 255], size=(h, w)).astype(np.uint8)]
-    for img in imgs:
-        img = np.ascontiguousarray(img)
-        for t in (1, 7, 20, 21, 60, 254, 255):
-            assert hostsim.hs_fast_quad_check(ptr(img), img.shape[1], img.shape[0], img.shape[1], t) == 0, t
-
-
 def test_fast_atan2_and_harris(hostsim):
     rng = np.random.default_rng(2)
     ys = rng.integers(-60000, 60000, 5000).astype(np.float32)
