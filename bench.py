@@ -619,6 +619,14 @@ def run_b200(a):
                 st["algorithmic_gflop"] = round(cheir_flop / 1e9, 3)
                 st["fp64_tflops"] = round(cheir_flop / (tms * 1e-3) / 1e12, 3)
                 st["frac_of_fp64_peak"] = round(cheir_flop / (tms * 1e-3) / max(pipe["fp64_mul_add_flops"], 1.0), 4)
+            if name in ("k_angle_pack", "k_brief"):
+                # gather stages: per keypoint the un-blurred 31x31 disc (709 B, k_angle_pack) or the blurred 37x48 steering window
+                # (1776 B, k_brief) plus the 32-B record written; the windows overlap and live in L2, so this is an L2-gather figure
+                per_kp = (709 + 32) if name == "k_angle_pack" else (37 * 48 + 32)
+                gbytes = float(np.sum(n_cur)) * per_kp
+                st["achieved_GBps"] = round(gbytes / (tms * 1e-3) / 1e9, 2)
+                st["frac_of_hbm_peak"] = round(st["achieved_GBps"] / peak, 4)
+                st["note"] = "L2 gather of overlapping windows; latency-bound"
             if name == "k_select":
                 # two retainBest passes over ~1 survivor per 130 px (3 comparisons per element for nth_element + partition) and the
                 # Harris response of 2 x quota survivors per level (7x7 block of Sobel products: ~1200 integer ops each)

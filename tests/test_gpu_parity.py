@@ -607,3 +607,14 @@ def test_tie_overflow_fails_loudly_and_mild_ties_equal_cv2(env):
     for k in ("pt", "angle", "response", "octave", "desc"):
         assert np.array_equal(f[k], ref[k]), k
     ctx.close()
+
+
+def test_pipe_rate_microbenchmarks_are_plausible(env):
+    """dvo_measure_peaks feeds bench.py's roofline denominators: fused rates about twice the unfused ones, FP32 about twice FP64,
+    the int8 tensor rate far above everything else, all within a factor of two of what a B200 at 1.9 GHz can do."""
+    p = env.native.measure_peaks(0)
+    assert 1.6 < p["fp32_fma_flops"] / p["fp32_mul_add_flops"] < 2.4
+    assert 1.6 < p["fp64_fma_flops"] / p["fp64_mul_add_flops"] < 2.4
+    assert 40e12 < p["fp32_fma_flops"] < 90e12 and 18e12 < p["fp64_fma_flops"] < 45e12
+    assert 2e12 < p["popc_per_s"] < 10e12
+    assert 2.0e15 < p["int8_tensor_ops"] < 5.0e15, p["int8_tensor_ops"]
