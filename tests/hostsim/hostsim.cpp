@@ -159,6 +159,7 @@ int hs_ring_has9_check() {
 float hs_harris(int a, int b, int c) { return harris_from_sums(a, b, c); }
 float hs_fast_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 int hs_five_point(const double* x1, const double* x2, double* models) { return five_point_solve(x1, x2, models); }
+void hs_null_space(const double* Q, double* basis) { null_space_5x9(Q, basis); }
 void hs_decompose(const double* E, double* R1, double* R2, double* t) { decompose_essential(E, R1, R2, t); }
 int hs_cheirality(const double* R, const double* t, double x1, double y1, double x2, double y2, double dist) {
     return cheirality_ok(R, t, x1, y1, x2, y2, dist) ? 1 : 0;

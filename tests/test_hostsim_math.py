@@ -1,8 +1,10 @@
 """CPU: the __host__ build of the per-element code the CUDA kernels execute (csrc/mathcore.cuh, csrc/select.cuh)
 against the oracle -- catches arithmetic mistakes before any GPU time is spent."""
 import ctypes
+import os
 
 import numpy as np
+import pytest
 
 from conftest import ptr
 from oracle import orb_np as O, pose_np as P
@@ -125,6 +127,65 @@ def test_five_point_solver(hostsim):
             worst.append(min(np.abs(e - r).max() for r in ref + [-r for r in ref]))
     # agreement with the LAPACK-based oracle is limited by the conditioning of the hidden-variable polynomial
     assert np.median(worst) < 1e-9 and np.mean(np.array(worst) < 1e-5) > 0.9
+
+
+def test_normalisation_is_cv2s_fused_form():
+    """cv.findEssentialMat normalises with fma(p, 1/f, -(c/f)) (MatExpr alpha*A + beta through the FMA3 convertTo kernel).  Probe:
+    a five-point call with K must be bit-identical to the call on pose_np.normalize_points' output with K = I; (p - c) / f is not."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    hits, plain_hits, n = 0, 0, 0
+    for K in (synth.camera_matrix(1280, 1024), np.array([[1173.854081, 0, 747.788206], [0, 1170.565083, 574.700374], [0, 0, 1.0]])):
+        for _ in range(30):
+            p1 = rng.uniform(0, 1280, (5, 2)).astype(np.float32).astype(np.float64)
+            p2 = (p1 + rng.normal(size=(5, 2)) * 8).astype(np.float32).astype(np.float64)
+            E0 = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.999, threshold=1.0)[0]
+            if E0 is None:
+                continue
+            n += 1
+            E1 = cv2.findEssentialMat(P.normalize_points(p1, K), P.normalize_points(p2, K), np.eye(3), method=cv2.RANSAC, prob=0.999, threshold=1.0)[0]
+            hits += int(E1 is not None and E1.shape == E0.shape and np.array_equal(E0, E1))
+            a = np.stack([(p1[:, 0] - K[0, 2]) / K[0, 0], (p1[:, 1] - K[1, 2]) / K[1, 1]], 1)
+            b = np.stack([(p2[:, 0] - K[0, 2]) / K[0, 0], (p2[:, 1] - K[1, 2]) / K[1, 1]], 1)
+            E2 = cv2.findEssentialMat(a, b, np.eye(3), method=cv2.RANSAC, prob=0.999, threshold=1.0)[0]
+            plain_hits += int(E2 is not None and E2.shape == E0.shape and np.array_equal(E0, E2))
+    if hits != n:
+        pytest.skip("this host's cv2 does not take the FMA3 convertTo path (%d of %d calls bit-identical)" % (hits, n))
+    assert plain_hits < n // 4
+
+
+def test_kernel_solver_works_in_cv2s_null_space_basis(hostsim):
+    """The hidden-variable coordinates (x, y, z) of a solution are coordinates in the null-space basis, so the basis is observable:
+    cv2 emits its solutions in the order cv::solvePoly finds the roots z of a polynomial that depends on the basis.  The numpy
+    prototype of cv2's basis (Gram-Schmidt of cv::SVD's fixed +-1/9 fill-in vectors) + Durand-Kerner reproduces cv2's ORDER; the
+    kernel solver's basis must span the same four vectors: every model the prototype finds, the kernel solver finds, with the
+    same z (models are emitted by ascending z)."""
+    cv2 = pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "analysis"))
+    import cv2_five_point_prototype as proto
+    rng = np.random.default_rng(4)
+    ordered = 0
+    for trial in range(25):
+        X = rng.uniform(-1, 1, (5, 3)) + np.array([0, 0, 4.0])
+        R, _ = cv2.Rodrigues(rng.normal(size=3) * 0.1)
+        t = rng.normal(size=3) * 0.3
+        x1 = np.ascontiguousarray(X[:, :2] / X[:, 2:])
+        Xc = (R @ X.T).T + t
+        x2 = np.ascontiguousarray(Xc[:, :2] / Xc[:, 2:])
+        Ecv = cv2.findEssentialMat(x1, x2, np.eye(3), method=cv2.RANSAC, prob=0.999, threshold=1.0)[0]
+        cvs = [Ecv[3 * i:3 * i + 3] for i in range(len(Ecv) // 3)]
+        ms = proto.five_point_cvlike(x1, x2, "rowmajor", False)
+        ordered += int(len(ms) == len(cvs) and all(min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-6 for a, b in zip(ms, cvs)))
+        # the basis itself: the kernel's four vectors against the prototype's, up to rounding
+        Q = np.array([[c * a, c * b, c, d * a, d * b, d, a, b, 1.0] for (a, b), (c, d) in zip(x1, x2)])
+        want = proto.basis_cv(Q)
+        got = np.zeros((4, 9))
+        hostsim.hs_null_space(ptr(np.ascontiguousarray(Q)), ptr(got))
+        assert np.abs(got - want).max() < 1e-9, trial
+    # with any other basis the order agrees on ~5 % of the samples (2 of 40 for the transposed conventions); ill-conditioned
+    # samples, where cv2's own root set moves with the last bit, keep this below 100 %
+    assert ordered >= 20, "prototype reproduced cv2's solution order on %d of 25 samples" % ordered
 
 
 def test_ransac_replay_with_kernel_solver_matches_golden(hostsim, golden):
