@@ -48,9 +48,9 @@ struct dvo_ctx {
     TensorMaps tmaps1{};
     bool lane1Ready = false;
     std::vector<void*> lane1Allocs;
-    cudaStream_t sOrb = nullptr, sPair = nullptr;
+    cudaStream_t sOrb = nullptr, sPair = nullptr, sImg = nullptr;
     cudaEvent_t evCall = nullptr, evOrbDone[2] = {nullptr, nullptr}, evPairsDone[2] = {nullptr, nullptr},
-                evCarryCopied[2] = {nullptr, nullptr};
+                evCarryCopied[2] = {nullptr, nullptr}, evImgDone[2] = {nullptr, nullptr};
     bool pairsPending[2] = {false, false}, carryPending[2] = {false, false};
     int carryLane = 0, lastLane = -1;
     bool pipeOutstanding = false;      // sPair holds work the caller's stream has not been joined with yet
@@ -394,12 +394,14 @@ int dvo_create(const dvo_config* cfg, int device, dvo_ctx** out) {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CK(cudaStreamCreateWithPriority(&ctx->sPair, cudaStreamNonBlocking, hi));
+            if (getenv("DVO_NO_IMAGE_STREAM") == nullptr) CK(cudaStreamCreateWithPriority(&ctx->sImg, cudaStreamNonBlocking, lo));
         }
         CK(cudaEventCreateWithFlags(&ctx->evCall, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&ctx->evOrbDone[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->evPairsDone[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->evCarryCopied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->evImgDone[i], cudaEventDisableTiming));
         }
     }
     CK(orb_kernels_init());
@@ -419,7 +421,9 @@ void dvo_destroy(dvo_ctx* ctx) {
         if (ctx->evOrbDone[i]) cudaEventDestroy(ctx->evOrbDone[i]);
         if (ctx->evPairsDone[i]) cudaEventDestroy(ctx->evPairsDone[i]);
         if (ctx->evCarryCopied[i]) cudaEventDestroy(ctx->evCarryCopied[i]);
+        if (ctx->evImgDone[i]) cudaEventDestroy(ctx->evImgDone[i]);
     }
+    if (ctx->sImg) cudaStreamDestroy(ctx->sImg);
     if (ctx->sOrb) cudaStreamDestroy(ctx->sOrb);
     if (ctx->sPair) cudaStreamDestroy(ctx->sPair);
     for (int i = 0; i < 2; ++i) {
@@ -807,15 +811,28 @@ static int sequence_step_pipelined(dvo_ctx* ctx, const uint8_t* frames, int n_ne
     const OrbBuffers& ob = L == 0 ? ctx->ob : ctx->ob1;
     const TensorMaps& tm = L == 0 ? ctx->tmaps : ctx->tmaps1;
     const int slot0 = fresh ? 0 : 1, nPairs = fresh ? n_new - 1 : n_new;
-    // ---- ORB stage
+    // ---- ORB stage.  Its image half (upload, pyramid, FAST) touches only lane L's pyramid and tile lists, which nothing has read
+    // since lane L's previous ORB stage ended: it goes on the low-priority stream sImg and may run under the keypoint half of
+    // the batch before (lane L ^ 1, stream sOrb).  The keypoint half overwrites lane L's features and therefore also waits for
+    // the pair stage and the carry copy that read them.
+    const bool serial = prof_enabled();     // per-kernel timing pass: no overlap between stages, no side streams
+    cudaStream_t sImg = (serial || ctx->sImg == nullptr) ? ctx->sOrb : ctx->sImg;
     CK(cudaEventRecord(ctx->evCall, st));
     CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCall, 0));
+    if (sImg != ctx->sOrb) {
+        CK(cudaStreamWaitEvent(sImg, ctx->evCall, 0));
+        CK(cudaStreamWaitEvent(sImg, ctx->evOrbDone[L], 0));      // lane L's previous ORB stage (no-op before the first one)
+    }
     if (ctx->pairsPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evPairsDone[L], 0));
-    const bool serial = prof_enabled();     // per-kernel timing pass: no overlap between stages, no side streams
     if (serial && !fresh && ctx->pairsPending[L ^ 1]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evPairsDone[L ^ 1], 0));
     if (ctx->carryPending[L]) CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evCarryCopied[L], 0));
-    if ((rc = load_frames_into(ctx, ob, frames, n_new, pitch, frame_stride, slot0, kind, ctx->sOrb)) != 0) return rc;
-    launch_orb(ctx->og, ob, &tm, ctx->useTma, slot0, n_new, ctx->sOrb, serial ? nullptr : &ctx->ss);
+    if ((rc = load_frames_into(ctx, ob, frames, n_new, pitch, frame_stride, slot0, kind, sImg)) != 0) return rc;
+    launch_orb_image(ctx->og, ob, &tm, ctx->useTma, slot0, n_new, sImg);
+    if (sImg != ctx->sOrb) {
+        CK(cudaEventRecord(ctx->evImgDone[L], sImg));
+        CK(cudaStreamWaitEvent(ctx->sOrb, ctx->evImgDone[L], 0));
+    }
+    launch_orb_keypoints(ctx->og, ob, slot0, n_new, ctx->sOrb, serial ? nullptr : &ctx->ss);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evOrbDone[L], ctx->sOrb));
     // ---- pair stage

@@ -26,9 +26,8 @@ constexpr int kFastBoxH = 40;
 constexpr int kTileListCap = (kTileW / 2) * (kTileH / 2);   // strict 3x3 NMS: no two survivors touch
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
-constexpr int kSelectSmallSmemBytes = 64 * 1024;     // k_select launch for the small pyramid levels (3 CTAs per SM)
-constexpr long long kSelectBigLevelPixels = 600000;  // levels above this go to the 160 KB launch (~0.1 B of list per pixel)
-constexpr int kSelectSmemBytes = 160 * 1024;   // k_select working array: 40960 candidates per level stay on chip
+constexpr long long kSelectBigLevelPixels = 600000;  // levels above this are launched apart from the small ones (two streams)
+constexpr int kSelectSmemBytes = 32 * 1024;    // k_select working window: lists up to 8192 candidates stay on chip, longer ones run from L2
 constexpr int kMaxModels = 10;
 
 struct LevelGeom {
@@ -168,6 +167,8 @@ struct SideStreams {
 // ---- launchers (orb_kernels.cu / pair_kernels.cu) ---------------------------------------------------------------
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st, const SideStreams* ss);
+void launch_orb_image(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots, cudaStream_t st);
+void launch_orb_keypoints(const OrbGeom& g, const OrbBuffers& b, int slot0, int nSlots, cudaStream_t st, const SideStreams* ss);
 void launch_build_undistort_map(const OrbGeom& g, const IngestBuffers& ib, const IngestParams& prm, cudaStream_t st);
 void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& ib, const uint8_t* d_src, int n, size_t pitch,
                    size_t frameStride, int slot0, cudaStream_t st);

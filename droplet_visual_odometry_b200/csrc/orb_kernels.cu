@@ -684,7 +684,12 @@ struct BlockAcc {
     __device__ int pair_swap_ge(int first, int last, T boundary) { return pair_swap<1>(first, last, boundary); }
 };
 
-constexpr int kSelectThreads = 1024;
+// A SMALL CTA on purpose: 128 threads and a 32 KB window (candidate lists that do not fit run from the L2-resident global working
+// copy).  Round 1 ran the big levels with 1024 threads and the whole 160 KB list on chip -- fastest alone (the passes are
+// barrier-bound either way), but such a CTA needs a whole SM's registers, starves behind the small CTAs of FAST / blur and blocks
+// them while it runs.  Small CTAs co-reside with everything, which is what lets the image half of the next batch run under
+// this kernel (dvo_api.cu, sequence_step_pipelined): 35.8 k -> 37.4 k pairs/s.
+constexpr int kSelectThreads = 128;
 constexpr int kSelectSeqTail = 32;    // ranges this short are finished by one warp running the scalar replay
 
 __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes, int level0) {
@@ -1206,8 +1211,16 @@ void launch_ingest(const OrbGeom& g, const OrbBuffers& b, const IngestBuffers& i
     ++g_launches;
 }
 
+// The ORB stage in two halves so that a sequence runner can put them on different streams: the IMAGE half (pyramid + FAST: dense,
+// issue-bound, small CTAs) reads only the frame and writes the pyramid and the tile lists; the KEYPOINT half (gather, select,
+// angle, blur, brief) is mostly latency-bound.
 void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots,
                 cudaStream_t st, const SideStreams* ss) {
+    launch_orb_image(g, b, tmaps, useTma, slot0, nSlots, st);
+    launch_orb_keypoints(g, b, slot0, nSlots, st, ss);
+}
+
+void launch_orb_image(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, bool useTma, int slot0, int nSlots, cudaStream_t st) {
     if (nSlots <= 0) return;
     for (int L = 1; L < g.nlevels; ++L) {
         const long long ctas8 = (long long)((g.lv[L].w + 127) / 128) * ((g.lv[L].h + 63) / 64) * nSlots;
@@ -1227,6 +1240,10 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
         ++g_launches;
         debug_sync("k_fast_nms", st);
     }
+}
+
+void launch_orb_keypoints(const OrbGeom& g, const OrbBuffers& b, int slot0, int nSlots, cudaStream_t st, const SideStreams* ss) {
+    if (nSlots <= 0) return;
     const bool fork = ss != nullptr && ss->side != nullptr;
     if (fork) {      // k_blur beside compact -> select -> angle
         cudaEventRecord(ss->evFork, st);
@@ -1239,8 +1256,7 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
     ++g_launches;
     debug_sync("k_gather", st);
     {
-        // Large levels: 1024 threads and the whole 160 KB working array (one CTA per SM).  Small levels (candidate lists
-        // that fit 64 KB): 512 threads, three CTAs per SM, on a second side stream so both groups run together.
+        // Large and small levels as two launches on two streams, so that the short small-level CTAs do not queue behind the long ones.
         int nBig = 0;
         while (nBig < g.nlevels && (long long)g.lv[nBig].w * g.lv[nBig].h > kSelectBigLevelPixels) ++nBig;
         const bool split = fork && ss->side2 != nullptr && nBig > 0 && nBig < g.nlevels;
@@ -1248,7 +1264,7 @@ void launch_orb(const OrbGeom& g, const OrbBuffers& b, const TensorMaps* tmaps, 
         if (split) {
             cudaEventRecord(ss->evFork2, st);
             cudaStreamWaitEvent(ss->side2, ss->evFork2, 0);
-            k_select<<<dim3(nSlots, g.nlevels - nBig), 512, kSelectSmallSmemBytes, ss->side2>>>(g, b, slot0, kSelectSmallSmemBytes, nBig);
+            k_select<<<dim3(nSlots, g.nlevels - nBig), kSelectThreads, kSelectSmemBytes, ss->side2>>>(g, b, slot0, kSelectSmemBytes, nBig);
             cudaEventRecord(ss->evJoin2, ss->side2);
             k_select<<<dim3(nSlots, nBig), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes, 0);
             cudaStreamWaitEvent(st, ss->evJoin2, 0);
