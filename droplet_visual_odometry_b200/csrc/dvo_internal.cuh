@@ -26,8 +26,9 @@ constexpr int kFastBoxH = 40;
 constexpr int kTileListCap = (kTileW / 2) * (kTileH / 2);   // strict 3x3 NMS: no two survivors touch
 constexpr int kFinSlack = 64;        // extra per-level room for ties at the Harris boundary
 constexpr int kMaxImageDim = 4096;   // 12-bit packed coordinates
-constexpr long long kSelectBigLevelPixels = 600000;  // levels above this are launched apart from the small ones (two streams)
-constexpr int kSelectSmemBytes = 32 * 1024;    // k_select working window: lists up to 8192 candidates stay on chip, longer ones run from L2
+constexpr int kSelectSmallSmemBytes = 64 * 1024;     // few-frame k_select launch for the small pyramid levels (3 CTAs per SM)
+constexpr long long kSelectBigLevelPixels = 600000;  // levels above this go to the big-level launch (~0.1 B of list per pixel)
+constexpr int kSelectSmemBytes = 160 * 1024;   // few-frame k_select working array: 40960 candidates per level stay on chip
 constexpr int kMaxModels = 10;
 
 struct LevelGeom {

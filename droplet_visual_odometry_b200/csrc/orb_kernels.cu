@@ -684,12 +684,16 @@ struct BlockAcc {
     __device__ int pair_swap_ge(int first, int last, T boundary) { return pair_swap<1>(first, last, boundary); }
 };
 
-// A SMALL CTA on purpose: 128 threads and a 32 KB window (candidate lists that do not fit run from the L2-resident global working
-// copy).  Round 1 ran the big levels with 1024 threads and the whole 160 KB list on chip -- fastest alone (the passes are
-// barrier-bound either way), but such a CTA needs a whole SM's registers, starves behind the small CTAs of FAST / blur and blocks
-// them while it runs.  Small CTAs co-reside with everything, which is what lets the image half of the next batch run under
-// this kernel (dvo_api.cu, sequence_step_pipelined): 35.8 k -> 37.4 k pairs/s.
-constexpr int kSelectThreads = 128;
+// Launch shapes.  Few frames in flight (two-frame calls, the high-density configuration): big CTAs -- 1024 threads and the whole
+// candidate list of a level in 160 KB of shared memory (512 threads / 64 KB for the small levels) -- finish a level fastest.
+// Batches: SMALL CTAs -- 128 threads and a 32 KB window, longer lists run from the L2-resident global working copy.  A big CTA
+// needs a whole SM's registers, starves behind the small CTAs of FAST / blur and blocks them while it runs; small CTAs co-reside
+// with everything, which is what lets the image half of the next batch run under this kernel (dvo_api.cu,
+// sequence_step_pipelined): 35.8 k -> 36.9 k pairs/s, and 148 x 8 of them also finish sooner than 444 big ones (0.52 -> 0.31 ms).
+constexpr int kSelectThreads = 1024;          // launch bound (64 registers)
+constexpr int kSelectBatchThreads = 128;
+constexpr int kSelectBatchSmemBytes = 32 * 1024;
+constexpr int kSelectBatchMinSlots = 24;
 constexpr int kSelectSeqTail = 32;    // ranges this short are finished by one warp running the scalar replay
 
 __global__ void __launch_bounds__(kSelectThreads) k_select(OrbGeom g, OrbBuffers b, int slot0, int smemBytes, int level0) {
@@ -1257,20 +1261,24 @@ void launch_orb_keypoints(const OrbGeom& g, const OrbBuffers& b, int slot0, int 
     debug_sync("k_gather", st);
     {
         // Large and small levels as two launches on two streams, so that the short small-level CTAs do not queue behind the long ones.
+        // Launch shape by the number of frames in flight (see kSelectBatch*).
         int nBig = 0;
         while (nBig < g.nlevels && (long long)g.lv[nBig].w * g.lv[nBig].h > kSelectBigLevelPixels) ++nBig;
         const bool split = fork && ss->side2 != nullptr && nBig > 0 && nBig < g.nlevels;
         ProfScope ps_(PF_SELECT, st);
+        const bool batch = nSlots >= kSelectBatchMinSlots;
+        const int bigThreads = batch ? kSelectBatchThreads : kSelectThreads, bigSmem = batch ? kSelectBatchSmemBytes : kSelectSmemBytes;
+        const int smallThreads = batch ? kSelectBatchThreads : 512, smallSmem = batch ? kSelectBatchSmemBytes : kSelectSmallSmemBytes;
         if (split) {
             cudaEventRecord(ss->evFork2, st);
             cudaStreamWaitEvent(ss->side2, ss->evFork2, 0);
-            k_select<<<dim3(nSlots, g.nlevels - nBig), kSelectThreads, kSelectSmemBytes, ss->side2>>>(g, b, slot0, kSelectSmemBytes, nBig);
+            k_select<<<dim3(nSlots, g.nlevels - nBig), smallThreads, smallSmem, ss->side2>>>(g, b, slot0, smallSmem, nBig);
             cudaEventRecord(ss->evJoin2, ss->side2);
-            k_select<<<dim3(nSlots, nBig), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes, 0);
+            k_select<<<dim3(nSlots, nBig), bigThreads, bigSmem, st>>>(g, b, slot0, bigSmem, 0);
             cudaStreamWaitEvent(st, ss->evJoin2, 0);
             ++g_launches;
         } else {
-            k_select<<<dim3(nSlots, g.nlevels), kSelectThreads, kSelectSmemBytes, st>>>(g, b, slot0, kSelectSmemBytes, 0);
+            k_select<<<dim3(nSlots, g.nlevels), bigThreads, bigSmem, st>>>(g, b, slot0, bigSmem, 0);
         }
     }
     ++g_launches;
