@@ -780,7 +780,8 @@ __global__ void k_copy_features(OrbGeom g, OrbBuffers a, OrbBuffers b, int src, 
     }
 }
 
-// Two-lane pipeline.  Per call: ORB of this batch on sOrb into lane L = (previous lane ^ 1); pair stage on sPair after it.
+// Two-lane, three-stage pipeline.  Per call: image half of this batch on sImg and keypoint half on sOrb into lane L = (previous
+// lane ^ 1); pair stage on sPair after it.
 // Hazards and the events that order them:
 //   ORB(L) overwrites lane L's features       -> waits evPairsDone[L] (pairs of the batch before last) and
 //                                                evCarryCopied[L] (the carry copy out of lane L issued with the last batch)

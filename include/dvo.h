@@ -60,9 +60,10 @@ typedef struct dvo_config {
     double distance_thresh;  /* cv.recoverPose distanceThresh, cv2 default 50                              */
     float ratio;             /* 0.75   (visual_odometry_v3.py:227)                                         */
     int use_tma;             /* 1: stage FAST tiles with TMA (default); 0: plain loads (debug)             */
-    int pipeline;            /* 1 (default): dvo_sequence / dvo_sequence_step overlap the ORB stage of one batch with the
-                                pair stage of the previous one on internal streams (second buffer set, allocated on
-                                first use); 0: every stage in order on the caller's stream                        */
+    int pipeline;            /* 1 (default): dvo_sequence / dvo_sequence_step run three batches at once on internal streams --
+                                image half (upload, pyramid, FAST) of batch s+1, keypoint half of batch s, pair stage of
+                                batch s-1 (second buffer set, allocated on first use); 0: every stage in order on the
+                                caller's stream                                                                       */
     int ransac_exhaustive;   /* 0 (default): cv.findEssentialMat's adaptive stop.  1: every one of ransac_max_iters hypotheses
                                 is solved and scored (whole-GPU batched solve + Sampson sweep; BASELINE configs[4] "all
                                 hypotheses scored"); the first model with the highest inlier count wins                */
